@@ -1,0 +1,470 @@
+// pnpl_core.cuh -- per-problem device routines of the CvxPnPL hot path.
+//
+// One *thread* owns one pose problem end to end (assembly -> 10x10 SDP by
+// Douglas-Rachford/ADMM -> pose extraction).  Every per-problem array lives in a
+// strided view (`Arr<S>`): element e of the problem owned by thread t sits at
+// base[e * S + t], so a warp touching "element e" reads 32 consecutive doubles
+// (bank-conflict free in shared memory, coalesced in global memory).
+//
+// Reference path being replaced (cvxpnpl.py, commit e20cca87):
+//   assembly      _point_constraints 20-104, _line_constraints 107-153,
+//                 B/A 548-549 | 579-580 | 623-624, Q 475
+//   SDP solve     scs.solve 485-489 on the static data of 387-448
+//   extraction    493-520, _constraint_ortho_det 221-343, _re6q3 156-218
+//
+// The routines are written as __host__ __device__ so the very same code can be
+// compiled by the host compiler inside tests/ (tests/host_harness.cpp) to debug
+// numerics without a GPU.  The product library only ever launches them as CUDA
+// kernels (pnpl_kernels.cu); there is no CPU execution path in the product.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CVX_HD __host__ __device__ __forceinline__
+#define CVX_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CVX_HD inline
+#define CVX_HD_NOINLINE
+#endif
+
+namespace cvx {
+
+// ---- status codes written per problem (low byte) -------------------------------
+enum : int32_t {
+    ST_OK = 0,            // converged to eps
+    ST_MAX_ITERS = 1,     // iteration cap hit: last iterate returned (SCS "solved_inaccurate")
+    ST_NAN = 2,           // non-finite data/iterate -> single NaN pose (cvxpnpl.py:493-498)
+    ST_SINGULAR = 3,      // singular system in the rank-4 recovery (LinAlgError at cvxpnpl.py:165/212)
+    ST_RANK0 = 4,         // no eigenvalue above 1e-3 (NotImplementedError at cvxpnpl.py:341)
+    ST_FLAG_NOT_CERTIFIED = 0x100  // |obj - dual obj| > eps (the warning of cvxpnpl.py:516-519)
+};
+
+template <int S>
+struct Arr {
+    double* p;
+    CVX_HD double& operator[](int e) const { return p[(size_t)e * S]; }
+    CVX_HD Arr<S> sub(int off) const { return Arr<S>{p + (size_t)off * S}; }
+};
+
+// runtime-strided read-only / write view for global scratch
+struct GArr {
+    double* p;
+    int64_t stride;
+    CVX_HD double& operator[](int e) const { return p[(int64_t)e * stride]; }
+};
+
+// packed lower-triangular (row-major) index of a symmetric matrix
+CVX_HD int sidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j + 1)) / 2 + i; }
+
+// ---- the 15 "triple" equalities (rows 2,3,5,8,9,11,13..21 of the reference's
+// A, cvxpnpl.py:401-435): sum_k s_k Z[i_k, j_k] = 0 over off-diagonal entries.
+// Each off-diagonal entry of Z belongs to exactly one triple.  (i > j always.)
+#define CVX_TRIPLES(X)                                     \
+    X(1, 0, +1, 4, 3, +1, 7, 6, +1)   /* r0.r1 */          \
+    X(2, 0, +1, 5, 3, +1, 8, 6, +1)   /* r0.r2 */          \
+    X(2, 1, +1, 5, 4, +1, 8, 7, +1)   /* r1.r2 */          \
+    X(3, 0, +1, 4, 1, +1, 5, 2, +1)   /* c0.c1 */          \
+    X(6, 0, +1, 7, 1, +1, 8, 2, +1)   /* c0.c2 */          \
+    X(6, 3, +1, 7, 4, +1, 8, 5, +1)   /* c1.c2 */          \
+    X(5, 1, +1, 4, 2, -1, 9, 6, -1)   /* (c0xc1)_0 = c2_0 */ \
+    X(3, 2, +1, 5, 0, -1, 9, 7, -1)                        \
+    X(4, 0, +1, 3, 1, -1, 9, 8, -1)                        \
+    X(8, 4, +1, 7, 5, -1, 9, 0, -1)   /* c1xc2 = c0 */     \
+    X(6, 5, +1, 8, 3, -1, 9, 1, -1)                        \
+    X(7, 3, +1, 6, 4, -1, 9, 2, -1)                        \
+    X(7, 2, +1, 8, 1, -1, 9, 3, -1)   /* c2xc0 = c1 */     \
+    X(8, 0, +1, 6, 2, -1, 9, 4, -1)                        \
+    X(6, 1, +1, 7, 0, -1, 9, 5, -1)
+
+// ---------------------------------------------------------------------------------
+// Assembly: correspondences -> Q (45 unique entries of the 9x9 block, packed lower)
+// and B (3x9, row-major).  Uses the Kronecker structure of the reference's rows:
+// every correspondence contributes  C'C += (P P') (x) W,  N'C += P' (x) W,
+// N'N += W  with the 3x3 weight  W = [p]x'[p]x = |p|^2 I - p p'  for a point with
+// bearing p (cvxpnpl.py:37, 53-102) and  W = n n'  for a line endpoint with
+// plane normal n (cvxpnpl.py:123-153).  Then B = (N'N)^-1 N'C and
+// Q = A'A = C'C - (N'C)' B   (cvxpnpl.py:623-624, 475; A never materialised).
+// ---------------------------------------------------------------------------------
+struct Accum {
+    double PPW[6][6];  // [sym idx of (a,c)][sym idx of (i,j)]  -> C'C
+    double PW[3][6];   // [a][sym idx (i,j)]                     -> N'C
+    double W[6];       // sym idx (i,j)                          -> N'N
+};
+
+CVX_HD int sym3(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j + 1)) / 2 + i; }
+
+CVX_HD void accum_init(Accum& a)
+{
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        a.W[i] = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a.PPW[i][j] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a.PW[i][j] = 0;
+}
+
+CVX_HD void accum_add(Accum& a, const double P[3], const double W[6])
+{
+    double PP[6] = {P[0] * P[0], P[1] * P[0], P[1] * P[1], P[2] * P[0], P[2] * P[1], P[2] * P[2]};
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        a.W[e] += W[e];
+#pragma unroll
+        for (int g = 0; g < 6; ++g) a.PPW[g][e] = fma(PP[g], W[e], a.PPW[g][e]);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) a.PW[g][e] = fma(P[g], W[e], a.PW[g][e]);
+    }
+}
+
+// general 3x3 inverse (adjugate / determinant); K is row-major
+CVX_HD void inv3(const double K[9], double Ki[9])
+{
+    double c00 = K[4] * K[8] - K[5] * K[7];
+    double c01 = K[5] * K[6] - K[3] * K[8];
+    double c02 = K[3] * K[7] - K[4] * K[6];
+    double det = K[0] * c00 + K[1] * c01 + K[2] * c02;
+    double id = 1.0 / det;
+    Ki[0] = c00 * id;
+    Ki[1] = (K[2] * K[7] - K[1] * K[8]) * id;
+    Ki[2] = (K[1] * K[5] - K[2] * K[4]) * id;
+    Ki[3] = c01 * id;
+    Ki[4] = (K[0] * K[8] - K[2] * K[6]) * id;
+    Ki[5] = (K[2] * K[3] - K[0] * K[5]) * id;
+    Ki[6] = c02 * id;
+    Ki[7] = (K[1] * K[6] - K[0] * K[7]) * id;
+    Ki[8] = (K[0] * K[4] - K[1] * K[3]) * id;
+}
+
+CVX_HD void bearing(const double Ki[9], double u, double v, double p[3])
+{
+    p[0] = fma(Ki[0], u, fma(Ki[1], v, Ki[2]));
+    p[1] = fma(Ki[3], u, fma(Ki[4], v, Ki[5]));
+    p[2] = fma(Ki[6], u, fma(Ki[7], v, Ki[8]));
+}
+
+// Q: 45 packed (9x9 lower, row-major), Bm: 27 (3x9 row-major).  Generic output
+// accessors so the caller can target registers, shared or global memory.
+// Returns false if the 3x3 normal system is singular / data non-finite.
+template <class QOut, class BOut>
+CVX_HD bool assemble(const double* K, const double* pts_2d, const double* pts_3d, int n_pts,
+                     const double* line_2d, const double* line_3d, int n_lines, QOut Q, BOut Bm)
+{
+    double Kl[9], Ki[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Kl[i] = K[i];
+    inv3(Kl, Ki);
+
+    Accum acc;
+    accum_init(acc);
+    for (int i = 0; i < n_pts; ++i) {
+        double p[3], P[3] = {pts_3d[3 * i], pts_3d[3 * i + 1], pts_3d[3 * i + 2]};
+        bearing(Ki, pts_2d[2 * i], pts_2d[2 * i + 1], p);
+        double n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        double W[6] = {n2 - p[0] * p[0], -p[1] * p[0], n2 - p[1] * p[1],
+                       -p[2] * p[0],     -p[2] * p[1], n2 - p[2] * p[2]};
+        accum_add(acc, P, W);
+    }
+    for (int i = 0; i < n_lines; ++i) {
+        double a[3], b[3];
+        bearing(Ki, line_2d[4 * i], line_2d[4 * i + 1], a);
+        bearing(Ki, line_2d[4 * i + 2], line_2d[4 * i + 3], b);
+        double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        double inv = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        n[0] *= inv; n[1] *= inv; n[2] *= inv;
+        double W[6] = {n[0] * n[0], n[1] * n[0], n[1] * n[1], n[2] * n[0], n[2] * n[1], n[2] * n[2]};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double P[3] = {line_3d[6 * i + 3 * e], line_3d[6 * i + 3 * e + 1], line_3d[6 * i + 3 * e + 2]};
+            accum_add(acc, P, W);
+        }
+    }
+    // inverse of the symmetric 3x3 N'N
+    double G[9] = {acc.W[0], acc.W[1], acc.W[3], acc.W[1], acc.W[2], acc.W[4], acc.W[3], acc.W[4], acc.W[5]};
+    double Gi[9];
+    inv3(G, Gi);
+    // N'C [i][3a+j] = PW[a][sym(i,j)];  B = Gi * N'C
+    double Bl[27];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s = fma(Gi[3 * i + k], acc.PW[a][sym3(k, j)], s);
+                Bl[9 * i + 3 * a + j] = s;
+            }
+    // Q[(3a+i),(3c+j)] = PPW[sym(a,c)][sym(i,j)] - sum_k N'C[k][3a+i] * B[k][3c+j]
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) {
+            const int a = r / 3, i = r % 3, cc = c / 3, j = c % 3;
+            double s = acc.PPW[sym3(a, cc)][sym3(i, j)];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s = fma(-acc.PW[a][sym3(k, i)], Bl[9 * k + 3 * cc + j], s);
+            Q[sidx(r, c)] = s;
+            ok = ok && isfinite(s);
+        }
+#pragma unroll
+    for (int i = 0; i < 27; ++i) {
+        Bm[i] = Bl[i];
+        ok = ok && isfinite(Bl[i]);
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------
+// Jacobi symmetric eigensolver on a packed 10x10 matrix held in a strided view,
+// rotating the columns of V (V[i*10+j] = component i of eigenvector j).  One
+// cyclic sweep over the 45 pivots; returns the off-diagonal square sum *before*
+// the sweep (so callers can decide whether another sweep is needed).
+// ---------------------------------------------------------------------------------
+template <int S>
+CVX_HD double jacobi_sweep(Arr<S> T, Arr<S> V)
+{
+    double off = 0.0;
+    for (int p = 0; p < 9; ++p) {
+        for (int q = p + 1; q < 10; ++q) {
+            const int ipq = sidx(q, p), ipp = sidx(p, p), iqq = sidx(q, q);
+            const double apq = T[ipq];
+            off = fma(apq, apq, off);
+            const double app = T[ipp], aqq = T[iqq];
+            // skip negligible pivots (also avoids 0/0)
+            if (fabs(apq) <= 1e-300 || fabs(apq) < 1e-17 * (fabs(app) + fabs(aqq))) continue;
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            const double c = 1.0 / sqrt(fma(t, t, 1.0));
+            const double s = t * c;
+            T[ipp] = fma(-t, apq, app);
+            T[iqq] = fma(t, apq, aqq);
+            T[ipq] = 0.0;
+            for (int k = 0; k < 10; ++k) {
+                if (k == p || k == q) continue;
+                const int ikp = sidx(k, p), ikq = sidx(k, q);
+                const double akp = T[ikp], akq = T[ikq];
+                T[ikp] = fma(c, akp, -s * akq);
+                T[ikq] = fma(s, akp, c * akq);
+            }
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                const double vkp = V[k * 10 + p], vkq = V[k * 10 + q];
+                V[k * 10 + p] = fma(c, vkp, -s * vkq);
+                V[k * 10 + q] = fma(s, vkp, c * vkq);
+            }
+        }
+    }
+    return off;
+}
+
+// T <- V' M V (packed), M packed symmetric.  M is first pulled into registers.
+template <int S>
+CVX_HD void rotate_into_basis(Arr<S> M, Arr<S> V, Arr<S> T)
+{
+    double m[55];
+#pragma unroll
+    for (int e = 0; e < 55; ++e) m[e] = M[e];
+    for (int j = 0; j < 10; ++j) {
+        double v[10], t[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = V[k * 10 + j];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) s = fma(m[sidx(i, k)], v[k], s);
+            t[i] = s;
+        }
+        for (int i = j; i < 10; ++i) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) s = fma(V[k * 10 + i], t[k], s);
+            T[sidx(i, j)] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// One Douglas-Rachford step of   min <Q,Z>  s.t.  Z in Affine (22 equalities of
+// cvxpnpl.py:387-448) and Z in PSD:
+//     Z  = P_psd(M)        (from the eigen-pairs lam, V of M)
+//     X  = P_aff(2 Z - M - Q/rho)
+//     M += alpha (X - Z)
+// Returns ||X - Z||_F^2, the fixed-point residual (primal residual X-Z and dual
+// residual rho (M+ - M)/alpha coincide up to scale).  Q/rho is read through `qr`
+// (45 packed entries of the 9x9 block).  Also returns Z in z[] (registers).
+//
+// P_aff in closed form: the 15 triples are mutually orthogonal and of equal norm,
+// so each is fixed by subtracting the signed mean of its three entries; the
+// remaining 7 equalities (rank 6) only touch the diagonal: Z99 = 1 and the 3x3
+// array D[r][c] = Z[3c+r, 3c+r] has unit row and column sums.
+// ---------------------------------------------------------------------------------
+template <int S, class QR>
+CVX_HD double dr_step(Arr<S> M, Arr<S> V, const double lam[10], QR qr, double alpha, double z[55])
+{
+#pragma unroll
+    for (int e = 0; e < 55; ++e) z[e] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        if (lam[j] > 0.0) {
+            double v[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) v[k] = V[k * 10 + j];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                const double lr = lam[j] * v[r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) z[sidx(r, c)] = fma(lr, v[c], z[sidx(r, c)]);
+            }
+        }
+    }
+    double res = 0.0;
+#define CVX_Q(i, j) (((i) < 9 && (j) < 9) ? qr[sidx(i, j)] : 0.0)
+#define CVX_TRI(i0, j0, s0, i1, j1, s1, i2, j2, s2)                                         \
+    {                                                                                        \
+        const int e0 = sidx(i0, j0), e1 = sidx(i1, j1), e2 = sidx(i2, j2);                  \
+        const double m0 = M[e0], m1 = M[e1], m2 = M[e2];                                    \
+        const double w0 = 2.0 * z[e0] - m0 - CVX_Q(i0, j0);                                 \
+        const double w1 = 2.0 * z[e1] - m1 - CVX_Q(i1, j1);                                 \
+        const double w2 = 2.0 * z[e2] - m2 - CVX_Q(i2, j2);                                 \
+        const double r = ((s0) * w0 + (s1) * w1 + (s2) * w2) * (1.0 / 3.0);                 \
+        const double d0 = w0 - (s0) * r - z[e0];                                            \
+        const double d1 = w1 - (s1) * r - z[e1];                                            \
+        const double d2 = w2 - (s2) * r - z[e2];                                            \
+        M[e0] = fma(alpha, d0, m0);                                                         \
+        M[e1] = fma(alpha, d1, m1);                                                         \
+        M[e2] = fma(alpha, d2, m2);                                                         \
+        res += 2.0 * (d0 * d0 + d1 * d1 + d2 * d2);                                         \
+    }
+    CVX_TRIPLES(CVX_TRI)
+#undef CVX_TRI
+    // diagonal block
+    {
+        double w[9], md[10];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            md[i] = M[sidx(i, i)];
+            w[i] = 2.0 * z[sidx(i, i)] - md[i] - qr[sidx(i, i)];
+        }
+        md[9] = M[sidx(9, 9)];
+        // D[r][c] = w[3c + r]; project onto unit row sums (over c) and column sums (over r)
+        double R[3], C[3], G = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) R[r] = w[r] + w[3 + r] + w[6 + r];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { C[c] = w[3 * c] + w[3 * c + 1] + w[3 * c + 2]; G += C[c]; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int i = 3 * c + r;
+                const double x = w[i] - (R[r] - 1.0) * (1.0 / 3.0) - (C[c] - 1.0) * (1.0 / 3.0)
+                                 + (G - 3.0) * (1.0 / 9.0);
+                const double d = x - z[sidx(i, i)];
+                M[sidx(i, i)] = fma(alpha, d, md[i]);
+                res = fma(d, d, res);
+            }
+        const double d9 = 1.0 - z[sidx(9, 9)];
+        M[sidx(9, 9)] = fma(alpha, d9, md[9]);
+        res = fma(d9, d9, res);
+    }
+#undef CVX_Q
+    return res;
+}
+
+// ---------------------------------------------------------------------------------
+// 3x3 orthogonal polar factor  U Vh  of a row-major 3x3 matrix (cvxpnpl.py:510-511,
+// SVD projection WITHOUT determinant correction).  Computed from the Jacobi
+// eigen-decomposition of A'A = W S^2 W':  U Vh = A W S^-1 W'.
+// ---------------------------------------------------------------------------------
+CVX_HD void polar3(const double A[9], double R[9])
+{
+    double G[6];  // packed lower of A'A
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j)
+            G[sym3(i, j)] = A[i] * A[j] + A[3 + i] * A[3 + j] + A[6 + i] * A[6 + j];
+    double W[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
+        if (off <= 1e-34 * (G[0] * G[0] + G[2] * G[2] + G[5] * G[5])) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2, k = 3 - p - q;
+            const double apq = G[sym3(q, p)];
+            if (apq == 0.0) continue;
+            const double app = G[sym3(p, p)], aqq = G[sym3(q, q)];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            const double c = 1.0 / sqrt(fma(t, t, 1.0)), s = t * c;
+            G[sym3(p, p)] = app - t * apq;
+            G[sym3(q, q)] = aqq + t * apq;
+            G[sym3(q, p)] = 0.0;
+            const double akp = G[sym3(k, p)], akq = G[sym3(k, q)];
+            G[sym3(k, p)] = c * akp - s * akq;
+            G[sym3(k, q)] = s * akp + c * akq;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double wp = W[3 * r + p], wq = W[3 * r + q];
+                W[3 * r + p] = c * wp - s * wq;
+                W[3 * r + q] = s * wp + c * wq;
+            }
+        }
+    }
+    // R = A * (W diag(1/sqrt(g)) W')
+    double is[3] = {1.0 / sqrt(G[0]), 1.0 / sqrt(G[2]), 1.0 / sqrt(G[5])};
+    double H[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            H[3 * i + j] = W[3 * i] * is[0] * W[3 * j] + W[3 * i + 1] * is[1] * W[3 * j + 1]
+                           + W[3 * i + 2] * is[2] * W[3 * j + 2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            R[3 * i + j] = A[3 * i] * H[j] + A[3 * i + 1] * H[3 + j] + A[3 * i + 2] * H[6 + j];
+}
+
+// From a 9-vector r_c (column-major vec of a near-rotation): SO(3)/O(3) projection,
+// translation t = -B r, objective r'Qr.  Writes R (row-major, world->camera) and t.
+// cvxpnpl.py:510-513, 520.
+template <class QIn, class BIn>
+CVX_HD double finish_pose(const double rc[9], QIn Q, BIn Bm, double* R_out, double* t_out)
+{
+    double Rp[9];
+    polar3(rc, Rp);  // Rp = projection of r_c.reshape(3,3) (row-major) = R' ; r = Rp.ravel()
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s = fma(Bm[9 * i + k], Rp[k], s);
+        t_out[i] = -s;
+    }
+    // returned R is the transpose (cvxpnpl.py:520)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R_out[3 * i + j] = Rp[3 * j + i];
+    double obj = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s = fma(Q[sidx(i, k)], Rp[k], s);
+        obj = fma(s, Rp[i], obj);
+    }
+    return obj;
+}
+
+}  // namespace cvx

@@ -1,0 +1,309 @@
+// pnpl_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of cvxpnpl_b200.
+//
+// Execution model: one thread per pose problem, 128 problems per CTA, one CTA per
+// SM (the per-problem state -- eigenbasis V 100, DR iterate M 55, rotated matrix
+// T 55 doubles -- fills 210 KB of the SM's shared memory in a [element][thread]
+// layout).  Nothing but the correspondences (in) and the poses (out) touches HBM;
+// Q/rho (45 doubles per problem) is parked in an L2-resident scratch.
+// See DESIGN.md for the layout and the roofline discussion.
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cvxpnpl_b200.h"
+#include "pnpl_core.cuh"
+#include "pnpl_extract.cuh"
+#include "pnpl_solve.cuh"
+
+namespace {
+
+constexpr int NT = 128;                    // problems (threads) per CTA
+constexpr int SMEM_DOUBLES = 210;          // V 100 + M 55 + T 55
+constexpr size_t SMEM_BYTES = (size_t)NT * SMEM_DOUBLES * sizeof(double);
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* msg)
+{
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+using cvx::Opts;
+
+__device__ __forceinline__ const double* problem_K(const cvxpnpl_b200_desc& d, int64_t b)
+{
+    return d.k_batched ? d.K + 9 * b : d.K;
+}
+
+// ---------------------------------------------------------------------------------
+// Fused kernel: assembly -> SDP -> extraction, one thread per problem.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, int64_t ws_stride)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * NT + tid;
+    if (b >= d.batch) return;
+
+    cvx::Arr<NT> V{smem + tid};
+    cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
+    cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
+    cvx::GArr qr{d.workspace + b, ws_stride};
+
+    cvx::Problem pr;
+    pr.K = problem_K(d, b);
+    pr.pts_2d = d.pts_2d + b * 2 * d.n_pts;
+    pr.pts_3d = d.pts_3d + b * 3 * d.n_pts;
+    pr.line_2d = d.line_2d + b * 4 * d.n_lines;
+    pr.line_3d = d.line_3d + b * 6 * d.n_lines;
+    pr.n_pts = d.n_pts;
+    pr.n_lines = d.n_lines;
+
+    cvx::Result rs;
+    cvx::solve_problem(pr, o, V, M, T, qr, d.R + b * 36, d.t + b * 12, d.Z ? d.Z + b * 100 : nullptr, rs);
+    d.n_poses[b] = rs.n_poses;
+    d.status[b] = rs.status;
+    d.iters[b] = rs.iters;
+    if (d.obj) {
+        d.obj[2 * b] = rs.pobj;
+        d.obj[2 * b + 1] = rs.dobj;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Stage kernels (parity testing of the individual reference functions)
+// ---------------------------------------------------------------------------------
+__global__ void assemble_kernel(cvxpnpl_b200_desc d, double* Q, double* Bmat)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.batch) return;
+    double q[45], bm[27];
+    cvx::assemble(problem_K(d, b), d.pts_2d + b * 2 * d.n_pts, d.pts_3d + b * 3 * d.n_pts, d.n_pts,
+                  d.line_2d + b * 4 * d.n_lines, d.line_3d + b * 6 * d.n_lines, d.n_lines, q, bm);
+    double* Qo = Q + b * 81;
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) Qo[9 * i + j] = q[cvx::sidx(i, j)];
+    for (int i = 0; i < 27; ++i) Bmat[b * 27 + i] = bm[i];
+}
+
+__global__ void __launch_bounds__(NT, 1)
+solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, int64_t ws_stride)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * NT + tid;
+    if (b >= d.batch) return;
+    cvx::Arr<NT> V{smem + tid};
+    cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
+    cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
+    cvx::GArr qr{d.workspace + b, ws_stride};
+    const double* Qi = Q + b * 81;
+    double nq = 0;
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) nq = fma(Qi[9 * i + j], Qi[9 * i + j], nq);
+    const double rho = o.rho_rel * sqrt(nq);
+    const bool finite = (rho > 0.0) && isfinite(rho);
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j <= i; ++j) qr[cvx::sidx(i, j)] = 0.5 * (Qi[9 * i + j] + Qi[9 * j + i]) / rho;
+    double lam[10];
+    bool converged = false;
+    int it = 0;
+    int32_t status = cvx::ST_NAN;
+    if (finite) {
+        it = cvx::dr_solve(V, M, T, qr, o, lam, converged);
+        status = converged ? cvx::ST_OK : cvx::ST_MAX_ITERS;
+        for (int j = 0; j < 10; ++j)
+            if (!isfinite(lam[j])) status = cvx::ST_NAN;
+    }
+    const double dobj = (status != cvx::ST_NAN) ? cvx::dual_objective(V, lam, qr, rho) : nan("");
+    if (d.Z) cvx::write_Z(V, lam, status == cvx::ST_NAN, d.Z + b * 100);
+    if (d.status) d.status[b] = status;
+    if (d.iters) d.iters[b] = it;
+    if (d.obj) {
+        d.obj[2 * b] = nan("");
+        d.obj[2 * b + 1] = dobj;
+    }
+}
+
+// extraction stage: eigen-decomposition of the given Z (cold Jacobi), then the
+// shared extraction routine.
+constexpr int NT_X = 64;
+__global__ void __launch_bounds__(NT_X)
+extract_kernel(cvxpnpl_b200_desc d, const double* Z, const double* Q, const double* Bmat,
+               const double* dobj_in, double eps)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * NT_X + tid;
+    if (b >= d.batch) return;
+    cvx::Arr<NT_X> V{smem + tid};
+    cvx::Arr<NT_X> Qs{smem + (size_t)100 * NT_X + tid};   // 45
+    cvx::Arr<NT_X> Bs{smem + (size_t)145 * NT_X + tid};   // 27
+    cvx::Arr<NT_X> T{smem + (size_t)172 * NT_X + tid};    // 55, later scratch
+    const double* Zi = Z + b * 100;
+    int32_t status = cvx::ST_OK;
+    for (int i = 0; i < 10; ++i) {
+        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
+        for (int j = 0; j <= i; ++j) {
+            const double z = 0.5 * (Zi[10 * i + j] + Zi[10 * j + i]);
+            if (!isfinite(z)) status = cvx::ST_NAN;
+            T[cvx::sidx(i, j)] = z;
+        }
+    }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j <= i; ++j) Qs[cvx::sidx(i, j)] = Q[b * 81 + 9 * i + j];
+    for (int i = 0; i < 27; ++i) Bs[i] = Bmat[b * 27 + i];
+    double lam[10];
+    if (status == cvx::ST_OK) {
+        for (int s = 0; s < 40; ++s) {
+            double dg = 0;
+            for (int j = 0; j < 10; ++j) dg = fma(T[cvx::sidx(j, j)], T[cvx::sidx(j, j)], dg);
+            const double off = cvx::jacobi_sweep(T, V);
+            if (!(off > 1e-32 * dg)) break;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) lam[j] = T[cvx::sidx(j, j)];
+    double pobj = nan("");
+    const bool have_d = dobj_in != nullptr;
+    const double dobj = have_d ? dobj_in[b] : nan("");
+    int np = cvx::extract_poses(V, lam, Qs, Bs, status, dobj, have_d ? eps : -1.0, d.R + b * 36,
+                                d.t + b * 12, pobj);
+    d.n_poses[b] = np;
+    d.status[b] = status;
+    if (d.obj) {
+        d.obj[2 * b] = pobj;
+        d.obj[2 * b + 1] = dobj;
+    }
+}
+
+int check_common(const cvxpnpl_b200_desc* d)
+{
+    if (!d) return fail(-1, "null descriptor");
+    if (d->batch < 0) return fail(-2, "negative batch");
+    if (d->n_pts < 0 || d->n_lines < 0) return fail(-3, "negative correspondence count");
+    return 0;
+}
+
+Opts make_opts(const cvxpnpl_b200_desc* d)
+{
+    Opts o;
+    const double eps = d->eps > 0 ? d->eps : 1e-9;
+    o.eps2 = eps * eps;
+    o.alpha = d->alpha > 0 ? d->alpha : 1.0;
+    o.rho_rel = d->rho_rel > 0 ? d->rho_rel : 0.02;
+    o.max_iters = d->max_iters > 0 ? d->max_iters : 2500;
+    o.sweeps = d->sweeps > 0 ? d->sweeps : 1;
+    return o;
+}
+
+int64_t ws_stride_for(int64_t batch) { return ((batch + NT - 1) / NT) * NT; }
+
+}  // namespace
+
+extern "C" {
+
+const char* cvxpnpl_b200_version(void) { return "cvxpnpl_b200 0.1.0 (sm_100a)"; }
+const char* cvxpnpl_b200_last_error(void) { return g_err; }
+int cvxpnpl_b200_last_launch_count(void) { return g_launches; }
+
+size_t cvxpnpl_b200_workspace_bytes(int64_t batch)
+{
+    if (batch <= 0) return 0;
+    return (size_t)ws_stride_for(batch) * 45 * sizeof(double);
+}
+
+int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
+{
+    g_launches = 0;
+    if (int rc = check_common(d)) return rc;
+    if (d->batch == 0) return 0;
+    if (d->n_pts + d->n_lines <= 0) return fail(-4, "no correspondences");
+    if (!d->K || (d->n_pts && (!d->pts_2d || !d->pts_3d)) || (d->n_lines && (!d->line_2d || !d->line_3d)))
+        return fail(-5, "null input pointer");
+    if (!d->R || !d->t || !d->n_poses || !d->status || !d->iters) return fail(-6, "null output pointer");
+    if (!d->workspace || d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch))
+        return fail(-7, "workspace too small");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(solve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SMEM_BYTES);
+        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t blocks = (d->batch + NT - 1) / NT;
+    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d),
+                                                                                  ws_stride_for(d->batch));
+    g_launches = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
+int cvxpnpl_b200_assemble(const cvxpnpl_b200_desc* d, double* Q, double* Bmat, void* stream)
+{
+    g_launches = 0;
+    if (int rc = check_common(d)) return rc;
+    if (d->batch == 0) return 0;
+    if (!Q || !Bmat || !d->K) return fail(-5, "null pointer");
+    if (d->n_pts + d->n_lines <= 0) return fail(-4, "no correspondences");
+    const int64_t blocks = (d->batch + 127) / 128;
+    assemble_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*d, Q, Bmat);
+    g_launches = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
+int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* stream)
+{
+    g_launches = 0;
+    if (int rc = check_common(d)) return rc;
+    if (d->batch == 0) return 0;
+    if (!Q) return fail(-5, "null Q");
+    if (!d->workspace || d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch))
+        return fail(-7, "workspace too small");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(solve_sdp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SMEM_BYTES);
+        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t blocks = (d->batch + NT - 1) / NT;
+    solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d), Q,
+                                                                                ws_stride_for(d->batch));
+    g_launches = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
+int cvxpnpl_b200_extract(const cvxpnpl_b200_desc* d, const double* Z, const double* Q, const double* Bmat,
+                         const double* dobj, void* stream)
+{
+    g_launches = 0;
+    if (int rc = check_common(d)) return rc;
+    if (d->batch == 0) return 0;
+    if (!Z || !Q || !Bmat) return fail(-5, "null input pointer");
+    if (!d->R || !d->t || !d->n_poses || !d->status) return fail(-6, "null output pointer");
+    const size_t smem = (size_t)NT_X * 227 * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t blocks = (d->batch + NT_X - 1) / NT_X;
+    const double eps = d->eps > 0 ? d->eps : 1e-9;
+    extract_kernel<<<(unsigned)blocks, NT_X, smem, (cudaStream_t)stream>>>(*d, Z, Q, Bmat, dobj, eps);
+    g_launches = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

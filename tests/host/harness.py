@@ -1,0 +1,60 @@
+"""Builds and binds tests/host/host_harness.cpp (test-only host compilation of the
+device routines; see the header of that file)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
+_SO = os.path.join(_HERE, "_build", "libhost_harness.so")
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_lib = None
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(_HERE, "host_harness.cpp")] + [
+            os.path.join(_ROOT, "cvxpnpl_b200", "csrc", f) for f in ("pnpl_core.cuh", "pnpl_extract.cuh", "pnpl_solve.cuh")]
+        if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+            os.makedirs(os.path.dirname(_SO), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _SO, srcs[0]])
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def solve(d, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0):
+    lib = load()
+    B, n_pts, n_lines = d["pts_2d"].shape[0], d["pts_2d"].shape[1], d["line_2d"].shape[1]
+    c = {k: np.ascontiguousarray(d[k], dtype=np.float64) for k in ("K", "pts_2d", "pts_3d", "line_2d", "line_3d")}
+    R, t = np.empty((B, 4, 3, 3)), np.empty((B, 4, 3))
+    n, st, it = (np.empty(B, np.int32) for _ in range(3))
+    obj, Z = np.empty((B, 2)), np.empty((B, 10, 10))
+    lib.host_solve(ctypes.c_int64(B), n_pts, n_lines, _p(c["K"]), int(c["K"].ndim == 3), _p(c["pts_2d"]),
+                   _p(c["pts_3d"]), _p(c["line_2d"]), _p(c["line_3d"]), ctypes.c_double(eps), max_iters, sweeps,
+                   ctypes.c_double(rho_rel), ctypes.c_double(alpha), _p(R), _p(t), n.ctypes.data_as(_ip),
+                   st.ctypes.data_as(_ip), it.ctypes.data_as(_ip), _p(obj), _p(Z))
+    return dict(R=R, t=t, n_poses=n, status=st, iters=it, obj=obj, Z=Z)
+
+
+def extract(Z, Q, Bm):
+    lib = load()
+    Z, Q, Bm = (np.ascontiguousarray(x, dtype=np.float64) for x in (Z, Q, Bm))
+    R, t, st = np.empty((4, 3, 3)), np.empty((4, 3)), np.zeros(1, np.int32)
+    n = lib.host_extract(_p(Z), _p(Q), _p(Bm), _p(R), _p(t), st.ctypes.data_as(_ip))
+    return n, R, t, int(st[0])
+
+
+def quartic(c):
+    lib = load()
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    x = np.empty(4)
+    n = lib.host_quartic(_p(c), _p(x))
+    return x[:n]

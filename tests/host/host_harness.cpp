@@ -1,0 +1,74 @@
+// tests/host/host_harness.cpp -- DEBUG/TEST ONLY.  Compiles the per-problem device
+// routines (cvxpnpl_b200/csrc/*.cuh, written __host__ __device__) with the host
+// compiler so the numerics of the CUDA path can be exercised by the CPU test suite
+// (`-m "not gpu"`) where no GPU exists.  It is NOT part of the product, is never
+// loaded by cvxpnpl_b200/, and is not a fallback: the product library fails loudly
+// without CUDA.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../cvxpnpl_b200/csrc/pnpl_solve.cuh"
+
+extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
+                          const double* pts_2d, const double* pts_3d, const double* line_2d,
+                          const double* line_3d, double eps, int max_iters, int sweeps, double rho_rel,
+                          double alpha, double* R, double* t, int32_t* n_poses, int32_t* status,
+                          int32_t* iters, double* obj, double* Z)
+{
+    cvx::Opts o;
+    o.eps2 = eps * eps;
+    o.alpha = alpha > 0 ? alpha : 1.0;
+    o.rho_rel = rho_rel > 0 ? rho_rel : 0.02;
+    o.max_iters = max_iters > 0 ? max_iters : 2500;
+    o.sweeps = sweeps > 0 ? sweeps : 1;
+    std::vector<double> V(100), M(55), T(55), qr(45);
+    for (int64_t b = 0; b < B; ++b) {
+        cvx::Problem pr;
+        pr.K = k_batched ? K + 9 * b : K;
+        pr.pts_2d = pts_2d + b * 2 * n_pts;
+        pr.pts_3d = pts_3d + b * 3 * n_pts;
+        pr.line_2d = line_2d + b * 4 * n_lines;
+        pr.line_3d = line_3d + b * 6 * n_lines;
+        pr.n_pts = n_pts;
+        pr.n_lines = n_lines;
+        cvx::Result rs;
+        cvx::solve_problem(pr, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{M.data()}, cvx::Arr<1>{T.data()},
+                           qr.data(), R + b * 36, t + b * 12, Z ? Z + b * 100 : nullptr, rs);
+        n_poses[b] = rs.n_poses;
+        status[b] = rs.status;
+        iters[b] = rs.iters;
+        if (obj) {
+            obj[2 * b] = rs.pobj;
+            obj[2 * b + 1] = rs.dobj;
+        }
+    }
+    return 0;
+}
+
+extern "C" int host_extract(const double* Zin, const double* Q9, const double* Bm, double* R, double* t,
+                            int32_t* status)
+{
+    std::vector<double> V(100), T(55), Qs(45);
+    for (int i = 0; i < 10; ++i) {
+        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j);
+        for (int j = 0; j <= i; ++j) T[cvx::sidx(i, j)] = 0.5 * (Zin[10 * i + j] + Zin[10 * j + i]);
+    }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j <= i; ++j) Qs[cvx::sidx(i, j)] = Q9[9 * i + j];
+    cvx::Arr<1> Va{V.data()}, Ta{T.data()};
+    for (int s = 0; s < 40; ++s) {
+        double dg = 0;
+        for (int j = 0; j < 10; ++j) dg += T[cvx::sidx(j, j)] * T[cvx::sidx(j, j)];
+        if (!(cvx::jacobi_sweep(Ta, Va) > 1e-32 * dg)) break;
+    }
+    double lam[10];
+    for (int j = 0; j < 10; ++j) lam[j] = T[cvx::sidx(j, j)];
+    int32_t st = 0;
+    double pobj;
+    int n = cvx::extract_poses(Va, lam, Qs.data(), Bm, st, 0.0, -1.0, R, t, pobj);
+    *status = st;
+    return n;
+}
+
+extern "C" int host_quartic(const double* c, double* x) { return cvx::quartic_real_parts(c, x); }

@@ -1,0 +1,207 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI, against the
+CPU oracle and the golden vectors from the verbatim reference.
+
+Tolerance (BASELINE.json north_star): rotation <= 1e-6 rad, relative translation
+<= 1e-6 against the oracle on identical inputs."""
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-6
+T_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def cb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import cvxpnpl_b200
+    return cvxpnpl_b200
+
+
+def _cuda(d, *keys):
+    return [torch.from_numpy(np.ascontiguousarray(d[k])).cuda() for k in keys]
+
+
+def _oracle_call(orc, d, i, n_pts, n_lines, **kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if n_pts and n_lines:
+            return orc.pnpl(d["pts_2d"][i], d["line_2d"][i], d["pts_3d"][i], d["line_3d"][i], d["K"], **kw)
+        if n_pts:
+            return orc.pnp(d["pts_2d"][i], d["pts_3d"][i], d["K"], **kw)
+        return orc.pnl(d["line_2d"][i], d["line_3d"][i], d["K"], **kw)
+
+
+def _solve(cb, d, n_pts, n_lines, **kw):
+    K = torch.from_numpy(d["K"]).cuda()
+    args = {}
+    if n_pts:
+        args.update(pts_2d=_cuda(d, "pts_2d")[0], pts_3d=_cuda(d, "pts_3d")[0])
+    if n_lines:
+        args.update(line_2d=_cuda(d, "line_2d")[0], line_3d=_cuda(d, "line_3d")[0])
+    res = cb.solve_batched(K, **args, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def test_library_loaded(cb):
+    from cvxpnpl_b200 import _lib
+    assert b"sm_100a" in _lib.load().cvxpnpl_b200_version()
+
+
+def test_assembly_matches_reference(cb, golden):
+    """cvxpnpl.py:20-153, 623-624, 475 -- against A'A and B computed by the verbatim
+    reference (tests/golden/synth.npz)."""
+    g = golden["synth"]
+    for name, n_pts, n_lines in (("pnp8", 8, 0), ("pnpl8_4", 8, 4), ("pnl6", 0, 6)):
+        for noise in (0, 1, 2):
+            key = f"{name}_s{noise}"
+            d = {k: g[f"{key}_{k}"] for k in ("pts_2d", "pts_3d", "line_2d", "line_3d", "K")}
+            Q, Bm = cb.assemble_batched(d["K"], d["pts_2d"] if n_pts else None, d["pts_3d"] if n_pts else None,
+                                        d["line_2d"] if n_lines else None, d["line_3d"] if n_lines else None)
+            torch.cuda.synchronize()
+            assert np.allclose(Q.cpu().numpy(), g[key + "_AtA"], rtol=0, atol=1e-13)
+            assert np.allclose(Bm.cpu().numpy(), g[key + "_B"], rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["pnp", "pnl", "pnpl"])
+def test_examples_known_answer(cb, golden, name):
+    """examples/pnp.py, pnl.py, pnpl.py through the reference-shaped scalar API."""
+    from cvxpnpl_b200 import synth
+    e = golden["examples"]
+    kw = {k[len(name) + 1:]: e[k] for k in e.files if k.startswith(name + "_")}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if name == "pnp":
+            poses = cb.pnp(pts_2d=kw["pts_2d"], pts_3d=kw["pts_3d"], K=kw["K"])
+        elif name == "pnl":
+            poses = cb.pnl(line_2d=kw["line_2d"], line_3d=kw["line_3d"], K=kw["K"])
+        else:
+            poses = cb.pnpl(pts_2d=kw["pts_2d"], line_2d=kw["line_2d"], pts_3d=kw["pts_3d"],
+                            line_3d=kw["line_3d"], K=kw["K"])
+    assert len(poses) == 1
+    R, t = poses[0]
+    assert R.shape == (3, 3) and t.shape == (3,)
+    # ground truth is printed with 8 decimals in the examples
+    assert synth.rotation_angle(kw["R_gt"], R) < 2e-7
+    assert np.linalg.norm(t - kw["t_gt"]) / np.linalg.norm(kw["t_gt"]) < 2e-7
+    # and the verbatim reference's output (golden)
+    assert synth.rotation_angle(kw["R"][0], R) < ROT_TOL
+    assert np.linalg.norm(t - kw["t"][0]) / np.linalg.norm(kw["t"][0]) < T_TOL
+
+
+@pytest.mark.parametrize("name,n_pts,n_lines", [("pnp8", 8, 0), ("pnpl8_4", 8, 4), ("pnl6", 0, 6)])
+def test_golden_synth(cb, golden, name, n_pts, n_lines):
+    """Poses returned by the verbatim reference (SDP solved by the oracle shim)."""
+    from cvxpnpl_b200 import synth
+    g = golden["synth"]
+    for noise in (0, 1, 2):
+        key = f"{name}_s{noise}"
+        d = {k: g[f"{key}_{k}"] for k in ("pts_2d", "pts_3d", "line_2d", "line_3d", "K")}
+        res = _solve(cb, d, n_pts, n_lines)
+        assert (res.n_poses.cpu().numpy() == g[key + "_n"]).all()
+        R, t = res.R.cpu().numpy()[:, 0], res.t.cpu().numpy()[:, 0]
+        ang = synth.rotation_angle(g[key + "_R"][:, 0], R)
+        terr = np.linalg.norm(t - g[key + "_t"][:, 0], axis=1) / np.linalg.norm(g[key + "_t"][:, 0], axis=1)
+        assert ang.max() < ROT_TOL, (key, ang)
+        assert terr.max() < T_TOL, (key, terr)
+
+
+@pytest.mark.parametrize("n_pts,n_lines,noise", [(8, 4, 1.0), (8, 0, 2.0), (8, 4, 0.0), (6, 0, 1.0), (0, 8, 1.0)])
+def test_parity_vs_oracle_seeded(cb, n_pts, n_lines, noise):
+    """Same seeded inputs through the CUDA path and the CPU oracle (restated SCS)."""
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    from oracle import kkt
+    B = 48
+    d = synth.make_batch(B, n_pts, n_lines, noise=noise, seed=11)
+    res = _solve(cb, d, n_pts, n_lines, return_Z=True)
+    R, t, Z = res.R.cpu().numpy(), res.t.cpu().numpy(), res.Z.cpu().numpy()
+    st = res.status.cpu().numpy()
+    assert ((st & 0xFF) == 0).all(), st
+    worst = [0.0, 0.0]
+    for i in range(B):
+        poses, aux = _oracle_call(orc, d, i, n_pts, n_lines, max_iters=200000, return_aux=True)
+        assert len(poses) == int(res.n_poses[i]) == 1
+        Ro, to = poses[0]
+        worst[0] = max(worst[0], float(synth.rotation_angle(Ro, R[i, 0])))
+        worst[1] = max(worst[1], float(np.linalg.norm(to - t[i, 0]) / np.linalg.norm(to)))
+        # solver-independent certificate on the CUDA Z, using the oracle's multipliers
+        cert = kkt.certificate(aux["Q"], Z[i], aux["info"]["y"])
+        assert cert["eq_res"] < 1e-7 and cert["psd_res"] < 1e-9 and cert["gap"] < 1e-7, cert
+    assert worst[0] < ROT_TOL and worst[1] < T_TOL, worst
+
+
+def test_full_size_properties(cb):
+    """BASELINE config 3 at full size (1e5 x PnPL 8+4): size-independent checks --
+    every R orthonormal, SDP objective == dual objective, noise-free ground truth
+    recovered, and the batch result identical to a re-solve of a random subset."""
+    from cvxpnpl_b200 import synth
+    B = 100_000
+    d = synth.make_batch(B, 8, 4, noise=0.0, seed=5)
+    res = _solve(cb, d, 8, 4)
+    R, t = res.R[:, 0], res.t[:, 0]
+    assert int((res.n_poses != 1).sum()) == 0
+    assert int(((res.status & 0xFF) != 0).sum()) == 0
+    I = torch.eye(3, dtype=torch.float64, device=R.device)
+    assert float((R @ R.transpose(1, 2) - I).abs().max()) < 1e-12
+    assert float((res.obj[:, 0] - res.obj[:, 1]).abs().max()) < 1e-8
+    ang, terr = synth.pose_error(d["R_gt"], d["t_gt"], R.cpu().numpy(), t.cpu().numpy())
+    assert ang.max() < 1e-6 and terr.max() < 1e-6, (ang.max(), terr.max())
+    idx = np.random.default_rng(0).choice(B, 257, replace=False)
+    sub = {k: (v[idx] if k != "K" else v) for k, v in d.items()}
+    res2 = _solve(cb, sub, 8, 4)
+    assert torch.equal(res2.R, res.R[idx]) and torch.equal(res2.t, res.t[idx])
+
+
+def test_edge_cases(cb):
+    """Empty batch, batch not a multiple of the CTA size, per-problem K, NaN input,
+    fewer than 3 elements through the plugin class."""
+    from cvxpnpl_b200 import synth
+    d = synth.make_batch(0, 8, 4, seed=1)
+    res = _solve(cb, d, 8, 4)
+    assert res.R.shape == (0, 4, 3, 3)
+    d = synth.make_batch(131, 8, 4, noise=1.0, seed=2)
+    res = _solve(cb, d, 8, 4)
+    dK = dict(d)
+    dK["K"] = np.repeat(d["K"][None], 131, axis=0)
+    resK = _solve(cb, dK, 8, 4)
+    assert torch.equal(res.R, resK.R) and torch.equal(res.t, resK.t)
+    bad = {k: v.copy() for k, v in d.items()}
+    bad["pts_2d"][5, 0, 0] = np.nan
+    resb = _solve(cb, bad, 8, 4)
+    assert int(resb.status[5]) & 0xFF == 2 and int(resb.n_poses[5]) == 1
+    assert torch.isnan(resb.R[5]).all()
+    ok = np.ones(131, bool)
+    ok[5] = False
+    assert torch.equal(resb.R[ok], res.R[ok])
+    poses = cb.CvxPnPL.estimate_pose(d["K"], pts_2d=d["pts_2d"][0, :2], pts_3d=d["pts_3d"][0, :2])
+    assert len(poses) == 1 and np.isnan(poses[0][0]).all()
+
+
+@pytest.mark.parametrize("name", ["pts4", "pts3", "lines3", "lines4", "p2l1", "coplanar8"])
+def test_extraction_degenerate(cb, golden, name):
+    """Multi-solution extraction (cvxpnpl.py:221-343, 156-218) replayed on the Z the
+    reference saw (golden), compared with the reference's candidate poses as sets."""
+    g = golden["degenerate"]
+    Z, Q, Bm = g[name + "_Z"], g[name + "_AtA"], g[name + "_B"]
+    res = cb.extract_batched(Z, Q, Bm)
+    torch.cuda.synchronize()
+    R, t = res.R.cpu().numpy(), res.t.cpu().numpy()
+    npo, st = res.n_poses.cpu().numpy(), res.status.cpu().numpy()
+    for i in range(len(Z)):
+        if not g[name + "_ok"][i]:
+            continue  # LinAlgError in the reference: an exactly singular system; no set to compare
+        n = int(g[name + "_n"][i])
+        assert npo[i] == n, (name, i, npo[i], n, st[i])
+        got = np.concatenate([R[i, :n].reshape(n, 9), t[i, :n]], axis=1)
+        exp = np.concatenate([g[name + "_R"][i, :n].reshape(n, 9), g[name + "_t"][i, :n]], axis=1)
+        dist = np.sort(np.abs(got[:, None, :] - exp[None, :, :]).max(-1).min(1))
+        # see tests/test_oracle.py::test_degenerate_extraction for the tolerance
+        assert dist[(n - 1) // 2] < 1e-6, (name, i, dist)
+        assert np.all(dist[: max(n - 1, 1)] < 1e-4), (name, i, dist)
