@@ -223,73 +223,162 @@ CVX_HD bool assemble(const double* K, const double* pts_2d, const double* pts_3d
 }
 
 // ---------------------------------------------------------------------------------
-// Jacobi symmetric eigensolver on a packed 10x10 matrix held in a strided view,
-// rotating the columns of V (V[i*10+j] = component i of eigenvector j).  One
-// cyclic sweep over the 45 pivots; returns the off-diagonal square sum *before*
-// the sweep (so callers can decide whether another sweep is needed).
+// Jacobi symmetric eigensolver, register resident.
+//
+// t[55] is the packed 10x10 matrix held in REGISTERS (every index below is a
+// compile-time constant after unrolling); V (eigenbasis, V[i*10+j] = component i
+// of eigenvector j) stays in the problem's strided shared-memory view.
+//
+// Pivot order: round-robin tournament, 9 rounds of 5 disjoint pairs.  The five
+// rotations of a round commute and their angles only depend on entries no other
+// rotation of the round touches, so all five (c, s) are computed up front
+// (instruction-level parallelism across the sqrt / divide chains) and then
+// applied.  V is updated once per THREE rounds: each row of V is loaded, rotated
+// by the 15 pending rotations in registers and stored, which cuts the
+// shared-memory traffic of the eigenvector update by 3x (600 instead of 1800
+// 8-byte accesses per sweep).
 // ---------------------------------------------------------------------------------
+CVX_HD constexpr int rr_a(int r, int k) { return k == 0 ? r : (r + k) % 9; }
+CVX_HD constexpr int rr_b(int r, int k) { return k == 0 ? 9 : (r + 9 - k) % 9; }
+CVX_HD constexpr int rr_p(int r, int k) { return rr_a(r, k) < rr_b(r, k) ? rr_a(r, k) : rr_b(r, k); }
+CVX_HD constexpr int rr_q(int r, int k) { return rr_a(r, k) < rr_b(r, k) ? rr_b(r, k) : rr_a(r, k); }
+
+// rotation angle for pivot (p,q): returns c, s and updates nothing
+CVX_HD void jacobi_cs(double app, double aqq, double apq, double& c, double& s, double& tn)
+{
+    const double d = aqq - app, b2 = 2.0 * apq;
+    const double h = sqrt(fma(d, d, b2 * b2));
+    const double den = fabs(d) + h;
+    // negligible pivot (also covers d = b2 = 0): identity rotation
+    const bool skip = !(fabs(apq) > 1e-18 * den) || !(den > 1e-300);
+    tn = skip ? 0.0 : copysign(1.0, d) * b2 / den;
+    c = 1.0 / sqrt(fma(tn, tn, 1.0));
+    s = tn * c;
+}
+
+// one sweep; returns the off-diagonal square sum seen at the pivots (before they
+// are annihilated)
 template <int S>
-CVX_HD double jacobi_sweep(Arr<S> T, Arr<S> V)
+CVX_HD double jacobi_sweep_reg(double t[55], Arr<S> V)
 {
     double off = 0.0;
-    for (int p = 0; p < 9; ++p) {
-        for (int q = p + 1; q < 10; ++q) {
-            const int ipq = sidx(q, p), ipp = sidx(p, p), iqq = sidx(q, q);
-            const double apq = T[ipq];
-            off = fma(apq, apq, off);
-            const double app = T[ipp], aqq = T[iqq];
-            // skip negligible pivots (also avoids 0/0)
-            if (fabs(apq) <= 1e-300 || fabs(apq) < 1e-17 * (fabs(app) + fabs(aqq))) continue;
-            const double theta = (aqq - app) / (2.0 * apq);
-            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-            const double c = 1.0 / sqrt(fma(t, t, 1.0));
-            const double s = t * c;
-            T[ipp] = fma(-t, apq, app);
-            T[iqq] = fma(t, apq, aqq);
-            T[ipq] = 0.0;
-            for (int k = 0; k < 10; ++k) {
-                if (k == p || k == q) continue;
-                const int ikp = sidx(k, p), ikq = sidx(k, q);
-                const double akp = T[ikp], akq = T[ikq];
-                T[ikp] = fma(c, akp, -s * akq);
-                T[ikq] = fma(s, akp, c * akq);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        double cs[15], sn[15];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+            const int r = 3 * g + rr;
+            double tn[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int p = rr_p(r, k), q = rr_q(r, k);
+                const double apq = t[sidx(q, p)];
+                off = fma(apq, apq, off);
+                jacobi_cs(t[sidx(p, p)], t[sidx(q, q)], apq, cs[5 * rr + k], sn[5 * rr + k], tn[k]);
             }
 #pragma unroll
-            for (int k = 0; k < 10; ++k) {
-                const double vkp = V[k * 10 + p], vkq = V[k * 10 + q];
-                V[k * 10 + p] = fma(c, vkp, -s * vkq);
-                V[k * 10 + q] = fma(s, vkp, c * vkq);
+            for (int k = 0; k < 5; ++k) {
+                const int p = rr_p(r, k), q = rr_q(r, k);
+                const double c = cs[5 * rr + k], s = sn[5 * rr + k];
+                const double apq = t[sidx(q, p)];
+                t[sidx(p, p)] = fma(-tn[k], apq, t[sidx(p, p)]);
+                t[sidx(q, q)] = fma(tn[k], apq, t[sidx(q, q)]);
+                t[sidx(q, p)] = 0.0;
+#pragma unroll
+                for (int m = 0; m < 10; ++m) {
+                    if (m == p || m == q) continue;
+                    const double amp = t[sidx(m, p)], amq = t[sidx(m, q)];
+                    t[sidx(m, p)] = fma(c, amp, -s * amq);
+                    t[sidx(m, q)] = fma(s, amp, c * amq);
+                }
             }
+        }
+        // apply the 15 pending rotations to every row of V
+        for (int row = 0; row < 10; ++row) {
+            double v[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) v[j] = V[row * 10 + j];
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const int r = 3 * g + rr;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const int p = rr_p(r, k), q = rr_q(r, k);
+                    const double c = cs[5 * rr + k], s = sn[5 * rr + k];
+                    const double vp = v[p], vq = v[q];
+                    v[p] = fma(c, vp, -s * vq);
+                    v[q] = fma(s, vp, c * vq);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 10; ++j) V[row * 10 + j] = v[j];
         }
     }
     return off;
 }
 
-// T <- V' M V (packed), M packed symmetric.  M is first pulled into registers.
+// t <- V' M V (packed, registers).  M is read from its shared-memory view with
+// compile-time offsets; columns of V are processed in blocks of 3 so every loaded
+// M entry feeds 6 FMAs and every loaded V column up to 3 dot products.
 template <int S>
-CVX_HD void rotate_into_basis(Arr<S> M, Arr<S> V, Arr<S> T)
+CVX_HD void rotate_into_basis_reg(Arr<S> M, Arr<S> V, double t[55])
 {
-    double m[55];
 #pragma unroll
-    for (int e = 0; e < 55; ++e) m[e] = M[e];
-    for (int j = 0; j < 10; ++j) {
-        double v[10], t[10];
+    for (int j0 = 0; j0 < 10; j0 += 3) {
+        constexpr int NB = 3;
+        double w[NB][10];  // w[jj] = M v_{j0+jj}
+        {
+            double vj[NB][10];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = V[k * 10 + j];
+            for (int jj = 0; jj < NB; ++jj)
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            double s = 0;
+                for (int k = 0; k < 10; ++k) {
+                    vj[jj][k] = (j0 + jj < 10) ? V[k * 10 + (j0 + jj < 10 ? j0 + jj : 9)] : 0.0;
+                    w[jj][k] = 0.0;
+                }
 #pragma unroll
-            for (int k = 0; k < 10; ++k) s = fma(m[sidx(i, k)], v[k], s);
-            t[i] = s;
+            for (int r = 0; r < 10; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) {
+                    const double m = M[sidx(r, c)];
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        if (j0 + jj >= 10) continue;
+                        w[jj][r] = fma(m, vj[jj][c], w[jj][r]);
+                        if (r != c) w[jj][c] = fma(m, vj[jj][r], w[jj][c]);
+                    }
+                }
         }
-        for (int i = j; i < 10; ++i) {
-            double s = 0;
 #pragma unroll
-            for (int k = 0; k < 10; ++k) s = fma(V[k * 10 + i], t[k], s);
-            T[sidx(i, j)] = s;
+        for (int i = j0; i < 10; ++i) {
+            double vi[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) vi[k] = V[k * 10 + i];
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) {
+                const int j = j0 + jj;
+                if (j >= 10 || j > i) continue;
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) sacc = fma(vi[k], w[jj][k], sacc);
+                t[sidx(i, j)] = sacc;
+            }
         }
     }
+}
+
+// memory-resident variant (cold start on a matrix held in a strided view); used by
+// the extraction stage kernel only.
+template <int S>
+CVX_HD double jacobi_sweep(Arr<S> T, Arr<S> V)
+{
+    double t[55];
+#pragma unroll
+    for (int e = 0; e < 55; ++e) t[e] = T[e];
+    const double off = jacobi_sweep_reg(t, V);
+#pragma unroll
+    for (int e = 0; e < 55; ++e) T[e] = t[e];
+    return off;
 }
 
 // ---------------------------------------------------------------------------------

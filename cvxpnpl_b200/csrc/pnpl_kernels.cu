@@ -113,7 +113,7 @@ solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, int64_t ws_stride
     int it = 0;
     int32_t status = cvx::ST_NAN;
     if (finite) {
-        it = cvx::dr_solve(V, M, T, qr, o, lam, converged);
+        it = cvx::dr_solve(V, M, qr, o, lam, converged);
         status = converged ? cvx::ST_OK : cvx::ST_MAX_ITERS;
         for (int j = 0; j < 10; ++j)
             if (!isfinite(lam[j])) status = cvx::ST_NAN;

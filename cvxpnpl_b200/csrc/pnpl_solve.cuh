@@ -35,7 +35,7 @@ struct Result {
 // converged eigen-decomposition of the final DR iterate M (Z = V max(lam,0) V').
 // ---------------------------------------------------------------------------------
 template <int S, class QR>
-CVX_HD int dr_solve(Arr<S> V, Arr<S> M, Arr<S> T, QR qr, const Opts& o, double lam[10], bool& converged)
+CVX_HD int dr_solve(Arr<S> V, Arr<S> M, QR qr, const Opts& o, double lam[10], bool& converged)
 {
     // start: Z0 = blkdiag(I/3, 1) (feasible for the diagonal block), U0 = 0
 #pragma unroll
@@ -48,30 +48,33 @@ CVX_HD int dr_solve(Arr<S> V, Arr<S> M, Arr<S> T, QR qr, const Opts& o, double l
     }
     converged = false;
     int it = 0;
-    while (it < o.max_iters) {
-        double z[55];
-        const double res = dr_step(M, V, lam, qr, o.alpha, z);
-        ++it;
-        if (!(res > o.eps2)) {  // also leaves on NaN
-            converged = (res <= o.eps2);
-            break;
+    bool iterating = true;
+    // One loop body serves both the DR iterations (one warm-started sweep each) and
+    // the final passes that drive the eigen-decomposition of the last iterate to
+    // full convergence, so the (large, unrolled) sweep code exists once.
+    for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+        if (iterating) {
+            double z[55];
+            const double res = dr_step(M, V, lam, qr, o.alpha, z);
+            ++it;
+            if (!(res > o.eps2)) {  // also leaves on NaN
+                converged = (res <= o.eps2);
+                iterating = false;
+            } else if (it >= o.max_iters) {
+                iterating = false;
+            }
         }
-        rotate_into_basis(M, V, T);
-        for (int s = 0; s < o.sweeps; ++s) jacobi_sweep(T, V);
+        double t[55];
+        rotate_into_basis_reg(M, V, t);
+        double off = 0.0, dg = 0.0;
+        for (int s = 0; s < (iterating ? o.sweeps : 1); ++s) off = jacobi_sweep_reg(t, V);
 #pragma unroll
-        for (int j = 0; j < 10; ++j) lam[j] = T[sidx(j, j)];
+        for (int j = 0; j < 10; ++j) {
+            lam[j] = t[sidx(j, j)];
+            dg = fma(lam[j], lam[j], dg);
+        }
+        if (!iterating && !(off > 1e-22 * dg)) break;
     }
-    // final, fully converged eigen-decomposition of M
-    rotate_into_basis(M, V, T);
-    for (int s = 0; s < 30; ++s) {
-        double dg = 0;
-#pragma unroll
-        for (int j = 0; j < 10; ++j) dg = fma(T[sidx(j, j)], T[sidx(j, j)], dg);
-        const double off = jacobi_sweep(T, V);
-        if (!(off > 1e-32 * dg)) break;
-    }
-#pragma unroll
-    for (int j = 0; j < 10; ++j) lam[j] = T[sidx(j, j)];
     return it;
 }
 
@@ -143,7 +146,7 @@ CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
     double lam[10];
     bool converged = false;
     if (finite) {
-        it = dr_solve(V, M, T, qr, o, lam, converged);
+        it = dr_solve(V, M, qr, o, lam, converged);
         status = converged ? ST_OK : ST_MAX_ITERS;
 #pragma unroll
         for (int j = 0; j < 10; ++j)

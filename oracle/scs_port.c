@@ -39,6 +39,9 @@ typedef struct {
     double A[M_ * N_];      /* dense row-major */
     double b[M_];
     double L[N_ * N_];      /* Cholesky factor of I + A^T A (lower) */
+    int rp[M_ + 1];         /* CSR of A (the reference ships A sparse: csc_matrix, cvxpnpl.py:442) */
+    int ci[M_ * N_];
+    double cv[M_ * N_];
     int ready;
 } scs_port_work;
 
@@ -85,6 +88,13 @@ int scs_port_setup(const double *A, const double *b)
             W.L[i * N_ + j] = s;
         }
     chol55(W.L);
+    int nz = 0;
+    for (int k = 0; k < M_; ++k) {
+        W.rp[k] = nz;
+        for (int j = 0; j < N_; ++j)
+            if (A[k * N_ + j] != 0.0) { W.ci[nz] = j; W.cv[nz] = A[k * N_ + j]; ++nz; }
+    }
+    W.rp[M_] = nz;
     W.ready = 1;
     return 0;
 }
@@ -93,8 +103,7 @@ static void Amul(const double *x, double *y)      /* y = A x */
 {
     for (int k = 0; k < M_; ++k) {
         double s = 0;
-        const double *r = W.A + k * N_;
-        for (int j = 0; j < N_; ++j) s += r[j] * x[j];
+        for (int e = W.rp[k]; e < W.rp[k + 1]; ++e) s += W.cv[e] * x[W.ci[e]];
         y[k] = s;
     }
 }
@@ -102,10 +111,8 @@ static void ATmul(const double *y, double *x)     /* x = A^T y */
 {
     for (int j = 0; j < N_; ++j) x[j] = 0;
     for (int k = 0; k < M_; ++k) {
-        const double *r = W.A + k * N_;
-        double yk = y[k];
-        if (yk != 0.0)
-            for (int j = 0; j < N_; ++j) x[j] += r[j] * yk;
+        const double yk = y[k];
+        for (int e = W.rp[k]; e < W.rp[k + 1]; ++e) x[W.ci[e]] += W.cv[e] * yk;
     }
 }
 
@@ -136,7 +143,8 @@ static void jacobi_eig(double *S, double *V)
         for (int p = 0; p < PS - 1; ++p)
             for (int q = p + 1; q < PS; ++q) {
                 double apq = S[p * PS + q];
-                if (apq == 0.0) continue;
+                /* negligible pivot: skip (also keeps denormals out of the loop) */
+                if (fabs(apq) <= 1e-20 * (fabs(S[p * PS + p]) + fabs(S[q * PS + q])) || fabs(apq) < 1e-290) continue;
                 double theta = (S[q * PS + q] - S[p * PS + p]) / (2 * apq);
                 double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
                 double c = 1 / sqrt(t * t + 1), s = t * c;

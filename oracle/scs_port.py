@@ -20,7 +20,7 @@ def build(force=False):
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         subprocess.check_call(
-            ["gcc", "-O2", "-fPIC", "-shared", "-o", _SO, src, "-lm"]
+            ["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", _SO, src, "-lm"]
         )
     return _SO
 
