@@ -24,7 +24,11 @@
 #if defined(__CUDACC__)
 #define CVX_HD __host__ __device__ __forceinline__
 #define CVX_HD_NOINLINE __host__ __device__ __noinline__
+// compiler-only scheduling fence: keeps ptxas from hoisting every load of an
+// unrolled region to its top (which blows the register budget)
+#define CVX_SCHED_FENCE() asm volatile("" ::: "memory")
 #else
+#define CVX_SCHED_FENCE() asm volatile("" ::: "memory")
 #define CVX_HD inline
 #define CVX_HD_NOINLINE
 #endif
@@ -45,6 +49,9 @@ template <int S>
 struct Arr {
     double* p;
     CVX_HD double& operator[](int e) const { return p[(size_t)e * S]; }
+    // load the compiler may not merge with an earlier load of the same element
+    // (used to stop it from keeping all of V in registers across unrolled phases)
+    CVX_HD double reload(int e) const { return *(volatile const double*)(p + (size_t)e * S); }
     CVX_HD Arr<S> sub(int off) const { return Arr<S>{p + (size_t)off * S}; }
 };
 
@@ -318,53 +325,58 @@ CVX_HD double jacobi_sweep_reg(double t[55], Arr<S> V)
 }
 
 // t <- V' M V (packed, registers).  M is read from its shared-memory view with
-// compile-time offsets; columns of V are processed in blocks of 3 so every loaded
-// M entry feeds 6 FMAs and every loaded V column up to 3 dot products.
-template <int S>
-CVX_HD void rotate_into_basis_reg(Arr<S> M, Arr<S> V, double t[55])
+// compile-time offsets; columns of V are processed in blocks of NB so every loaded
+// M entry feeds 2*NB FMAs and every loaded V column up to NB dot products.
+template <int S, int J0, int NB>
+CVX_HD void rotate_block(Arr<S> M, Arr<S> V, double t[55])
 {
+    double w[NB][10];  // w[jj] = M v_{J0+jj}
+    {
+        double vj[NB][10];
 #pragma unroll
-    for (int j0 = 0; j0 < 10; j0 += 3) {
-        constexpr int NB = 3;
-        double w[NB][10];  // w[jj] = M v_{j0+jj}
-        {
-            double vj[NB][10];
+        for (int jj = 0; jj < NB; ++jj)
 #pragma unroll
-            for (int jj = 0; jj < NB; ++jj)
+            for (int k = 0; k < 10; ++k) {
+                vj[jj][k] = V[k * 10 + J0 + jj];
+                w[jj][k] = 0.0;
+            }
 #pragma unroll
-                for (int k = 0; k < 10; ++k) {
-                    vj[jj][k] = (j0 + jj < 10) ? V[k * 10 + (j0 + jj < 10 ? j0 + jj : 9)] : 0.0;
-                    w[jj][k] = 0.0;
+        for (int r = 0; r < 10; ++r) {
+#pragma unroll
+            for (int c = 0; c <= r; ++c) {
+                const double m = M[sidx(r, c)];
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    w[jj][r] = fma(m, vj[jj][c], w[jj][r]);
+                    if (r != c) w[jj][c] = fma(m, vj[jj][r], w[jj][c]);
                 }
-#pragma unroll
-            for (int r = 0; r < 10; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) {
-                    const double m = M[sidx(r, c)];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        if (j0 + jj >= 10) continue;
-                        w[jj][r] = fma(m, vj[jj][c], w[jj][r]);
-                        if (r != c) w[jj][c] = fma(m, vj[jj][r], w[jj][c]);
-                    }
-                }
-        }
-#pragma unroll
-        for (int i = j0; i < 10; ++i) {
-            double vi[10];
-#pragma unroll
-            for (int k = 0; k < 10; ++k) vi[k] = V[k * 10 + i];
-#pragma unroll
-            for (int jj = 0; jj < NB; ++jj) {
-                const int j = j0 + jj;
-                if (j >= 10 || j > i) continue;
-                double sacc = 0.0;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) sacc = fma(vi[k], w[jj][k], sacc);
-                t[sidx(i, j)] = sacc;
             }
         }
     }
+#pragma unroll
+    for (int i = J0; i < 10; ++i) {
+        double vi[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) vi[k] = V.reload(k * 10 + i);
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+            if (J0 + jj > i) continue;
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) sacc = fma(vi[k], w[jj][k], sacc);
+            t[sidx(i, J0 + jj)] = sacc;
+        }
+        CVX_SCHED_FENCE();
+    }
+}
+
+template <int S>
+CVX_HD void rotate_into_basis_reg(Arr<S> M, Arr<S> V, double t[55])
+{
+    rotate_block<S, 0, 3>(M, V, t);
+    rotate_block<S, 3, 3>(M, V, t);
+    rotate_block<S, 6, 2>(M, V, t);
+    rotate_block<S, 8, 2>(M, V, t);
 }
 
 // memory-resident variant (cold start on a matrix held in a strided view); used by

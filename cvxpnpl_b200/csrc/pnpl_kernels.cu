@@ -1,10 +1,10 @@
 // pnpl_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of cvxpnpl_b200.
 //
 // Execution model: one thread per pose problem, 128 problems per CTA, one CTA per
-// SM (the per-problem state -- eigenbasis V 100, DR iterate M 55, rotated matrix
-// T 55 doubles -- fills 210 KB of the SM's shared memory in a [element][thread]
-// layout).  Nothing but the correspondences (in) and the poses (out) touches HBM;
-// Q/rho (45 doubles per problem) is parked in an L2-resident scratch.
+// SM.  The per-problem state -- eigenbasis V 100, DR iterate M 55, Q/rho 45
+// doubles -- fills 200 KB of the SM's shared memory in a [element][thread]
+// layout; the rotated matrix T (55) lives in registers.  Nothing but the
+// correspondences (in) and the poses (out) touches HBM.
 // See DESIGN.md for the layout and the roofline discussion.
 #include <cuda_runtime.h>
 
@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int NT = 128;                    // problems (threads) per CTA
-constexpr int SMEM_DOUBLES = 210;          // V 100 + M 55 + T 55
+constexpr int SMEM_DOUBLES = 200;          // V 100 + M 55 + Q/rho 45
 constexpr size_t SMEM_BYTES = (size_t)NT * SMEM_DOUBLES * sizeof(double);
 
 thread_local char g_err[512] = "";
@@ -41,7 +41,7 @@ __device__ __forceinline__ const double* problem_K(const cvxpnpl_b200_desc& d, i
 // ---------------------------------------------------------------------------------
 // Fused kernel: assembly -> SDP -> extraction, one thread per problem.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, int64_t ws_stride)
+__global__ void __launch_bounds__(NT, 1) solve_fused_kernel(cvxpnpl_b200_desc d, Opts o)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
@@ -50,8 +50,7 @@ __global__ void __launch_bounds__(NT, 1) solve_fused_kernel(cvxpnpl_b200_desc d,
 
     cvx::Arr<NT> V{smem + tid};
     cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
-    cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
-    cvx::GArr qr{d.workspace + b, ws_stride};
+    cvx::Arr<NT> QR{smem + (size_t)155 * NT + tid};
 
     cvx::Problem pr;
     pr.K = problem_K(d, b);
@@ -63,7 +62,7 @@ __global__ void __launch_bounds__(NT, 1) solve_fused_kernel(cvxpnpl_b200_desc d,
     pr.n_lines = d.n_lines;
 
     cvx::Result rs;
-    cvx::solve_problem(pr, o, V, M, T, qr, d.R + b * 36, d.t + b * 12, d.Z ? d.Z + b * 100 : nullptr, rs);
+    cvx::solve_problem(pr, o, V, M, QR, d.R + b * 36, d.t + b * 12, d.Z ? d.Z + b * 100 : nullptr, rs);
     d.n_poses[b] = rs.n_poses;
     d.status[b] = rs.status;
     d.iters[b] = rs.iters;
@@ -90,7 +89,7 @@ __global__ void assemble_kernel(cvxpnpl_b200_desc d, double* Q, double* Bmat)
 }
 
 __global__ void __launch_bounds__(NT, 1)
-solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, int64_t ws_stride)
+solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
@@ -98,8 +97,7 @@ solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, int64_t ws_stride
     if (b >= d.batch) return;
     cvx::Arr<NT> V{smem + tid};
     cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
-    cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
-    cvx::GArr qr{d.workspace + b, ws_stride};
+    cvx::Arr<NT> qr{smem + (size_t)155 * NT + tid};
     const double* Qi = Q + b * 81;
     double nq = 0;
     for (int i = 0; i < 9; ++i)
@@ -200,8 +198,6 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     return o;
 }
 
-int64_t ws_stride_for(int64_t batch) { return ((batch + NT - 1) / NT) * NT; }
-
 }  // namespace
 
 extern "C" {
@@ -212,8 +208,10 @@ int cvxpnpl_b200_last_launch_count(void) { return g_launches; }
 
 size_t cvxpnpl_b200_workspace_bytes(int64_t batch)
 {
-    if (batch <= 0) return 0;
-    return (size_t)ws_stride_for(batch) * 45 * sizeof(double);
+    // all per-problem state lives in shared memory and registers; the entry is
+    // kept so callers are ready for variants that need device scratch
+    (void)batch;
+    return 0;
 }
 
 int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
@@ -225,7 +223,8 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     if (!d->K || (d->n_pts && (!d->pts_2d || !d->pts_3d)) || (d->n_lines && (!d->line_2d || !d->line_3d)))
         return fail(-5, "null input pointer");
     if (!d->R || !d->t || !d->n_poses || !d->status || !d->iters) return fail(-6, "null output pointer");
-    if (!d->workspace || d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch))
+    if (d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch) ||
+        (cvxpnpl_b200_workspace_bytes(d->batch) && !d->workspace))
         return fail(-7, "workspace too small");
     static bool attr_set = false;
     if (!attr_set) {
@@ -235,8 +234,7 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         attr_set = true;
     }
     const int64_t blocks = (d->batch + NT - 1) / NT;
-    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d),
-                                                                                  ws_stride_for(d->batch));
+    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d));
     g_launches = 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
@@ -264,7 +262,8 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
     if (int rc = check_common(d)) return rc;
     if (d->batch == 0) return 0;
     if (!Q) return fail(-5, "null Q");
-    if (!d->workspace || d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch))
+    if (d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch) ||
+        (cvxpnpl_b200_workspace_bytes(d->batch) && !d->workspace))
         return fail(-7, "workspace too small");
     static bool attr_set = false;
     if (!attr_set) {
@@ -274,8 +273,7 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
         attr_set = true;
     }
     const int64_t blocks = (d->batch + NT - 1) / NT;
-    solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d), Q,
-                                                                                ws_stride_for(d->batch));
+    solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d), Q);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));

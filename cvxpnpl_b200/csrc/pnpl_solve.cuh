@@ -113,18 +113,19 @@ CVX_HD void write_Z(Arr<S> V, const double lam[10], bool is_nan, double* Zo)
         }
 }
 
-// Whole path for one problem.  V (100), M (55), T (55) are the problem's strided
-// work arrays; qr is 45 entries of scratch for Q/rho.
-template <int S, class QR>
-CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, QR qr,
+// Whole path for one problem.  V (100), M (55) and QR (45) are the problem's strided
+// work arrays (200 doubles per problem, all in shared memory in the CUDA kernel).
+template <int S>
+CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> QR,
                           double* R_out, double* t_out, double* Z_out, Result& rs)
 {
-    // ---- assembly (Q, B into the T / M regions, which are free for now) ----------
+    // ---- assembly: Q (45) and B (27) land in the V region, which is free until the
+    // DR loop initialises it; Q/rho goes to its own region ---------------------------
     double rho;
     bool finite;
     {
-        Arr<S> Qs = T;  // 45 of 55
-        Arr<S> Bs = M;  // 27 of 55
+        Arr<S> Qs = V;
+        Arr<S> Bs = V.sub(45);
         finite = assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
         double nq = 0;
 #pragma unroll
@@ -138,7 +139,7 @@ CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
         finite = finite && (rho > 0.0) && isfinite(rho);
         const double ir = 1.0 / rho;
 #pragma unroll
-        for (int e = 0; e < 45; ++e) qr[e] = Qs[e] * ir;
+        for (int e = 0; e < 45; ++e) QR[e] = Qs[e] * ir;
     }
 
     int32_t status = ST_NAN;
@@ -146,18 +147,18 @@ CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
     double lam[10];
     bool converged = false;
     if (finite) {
-        it = dr_solve(V, M, qr, o, lam, converged);
+        it = dr_solve(V, M, QR, o, lam, converged);
         status = converged ? ST_OK : ST_MAX_ITERS;
 #pragma unroll
         for (int j = 0; j < 10; ++j)
             if (!isfinite(lam[j])) status = ST_NAN;
     }
-    const double dobj = (status != ST_NAN) ? dual_objective(V, lam, qr, rho) : nan("");
+    const double dobj = (status != ST_NAN) ? dual_objective(V, lam, QR, rho) : nan("");
     if (Z_out) write_Z(V, lam, status == ST_NAN, Z_out);
 
-    // ---- extraction: Q and B are re-assembled (cheap) into the free M / T regions --
-    Arr<S> Qs = T;
-    Arr<S> Bs = M;
+    // ---- extraction: Q and B are re-assembled (cheap) into the now free M / QR regions
+    Arr<S> Qs = M;
+    Arr<S> Bs = QR;
     if (status != ST_NAN) assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
     double pobj;
     rs.n_poses = extract_poses(V, lam, Qs, Bs, status, dobj, sqrt(o.eps2), R_out, t_out, pobj);

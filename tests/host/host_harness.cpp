@@ -22,7 +22,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
     o.rho_rel = rho_rel > 0 ? rho_rel : 0.02;
     o.max_iters = max_iters > 0 ? max_iters : 2500;
     o.sweeps = sweeps > 0 ? sweeps : 1;
-    std::vector<double> V(100), M(55), T(55), qr(45);
+    std::vector<double> V(100), M(55), qr(45);
     for (int64_t b = 0; b < B; ++b) {
         cvx::Problem pr;
         pr.K = k_batched ? K + 9 * b : K;
@@ -33,8 +33,8 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
         pr.n_pts = n_pts;
         pr.n_lines = n_lines;
         cvx::Result rs;
-        cvx::solve_problem(pr, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{M.data()}, cvx::Arr<1>{T.data()},
-                           qr.data(), R + b * 36, t + b * 12, Z ? Z + b * 100 : nullptr, rs);
+        cvx::solve_problem(pr, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{M.data()}, cvx::Arr<1>{qr.data()},
+                           R + b * 36, t + b * 12, Z ? Z + b * 100 : nullptr, rs);
         n_poses[b] = rs.n_poses;
         status[b] = rs.status;
         iters[b] = rs.iters;
