@@ -33,6 +33,7 @@ class Desc(ctypes.Structure):
         ("sweeps", ctypes.c_int32),
         ("rho_rel", ctypes.c_double),
         ("alpha", ctypes.c_double),
+        ("sigma", ctypes.c_double),
         ("R", ctypes.c_void_p),
         ("t", ctypes.c_void_p),
         ("n_poses", ctypes.c_void_p),

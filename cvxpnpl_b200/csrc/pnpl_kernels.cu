@@ -1,10 +1,11 @@
 // pnpl_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of cvxpnpl_b200.
 //
 // Execution model: one thread per pose problem, 128 problems per CTA, one CTA per
-// SM.  The per-problem state -- eigenbasis V 100, DR iterate M 55, Q/rho 45
-// doubles -- fills 200 KB of the SM's shared memory in a [element][thread]
-// layout; the rotated matrix T (55) lives in registers.  Nothing but the
-// correspondences (in) and the poses (out) touches HBM.
+// SM.  The per-problem state -- eigenbasis V 100, DR iterate M 55, rotated matrix
+// T 55, eigenvalues 10 doubles -- fills 220 KB of the SM's shared memory in a
+// [element][thread] layout; during a Jacobi sweep T lives in registers.  Q/rho
+// (45 doubles per problem, read once per iteration) is parked in an L2-resident
+// scratch.  Nothing but the correspondences (in) and the poses (out) touches HBM.
 // See DESIGN.md for the layout and the roofline discussion.
 #include <cuda_runtime.h>
 
@@ -19,7 +20,7 @@
 namespace {
 
 constexpr int NT = 128;                    // problems (threads) per CTA
-constexpr int SMEM_DOUBLES = 200;          // V 100 + M 55 + Q/rho 45
+constexpr int SMEM_DOUBLES = 220;          // V 100 + M 55 + T 55 + lambda 10
 constexpr size_t SMEM_BYTES = (size_t)NT * SMEM_DOUBLES * sizeof(double);
 
 thread_local char g_err[512] = "";
@@ -38,20 +39,8 @@ __device__ __forceinline__ const double* problem_K(const cvxpnpl_b200_desc& d, i
     return d.k_batched ? d.K + 9 * b : d.K;
 }
 
-// ---------------------------------------------------------------------------------
-// Fused kernel: assembly -> SDP -> extraction, one thread per problem.
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) solve_fused_kernel(cvxpnpl_b200_desc d, Opts o)
+__device__ __forceinline__ cvx::Problem problem_at(const cvxpnpl_b200_desc& d, int64_t b)
 {
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x;
-    const int64_t b = (int64_t)blockIdx.x * NT + tid;
-    if (b >= d.batch) return;
-
-    cvx::Arr<NT> V{smem + tid};
-    cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
-    cvx::Arr<NT> QR{smem + (size_t)155 * NT + tid};
-
     cvx::Problem pr;
     pr.K = problem_K(d, b);
     pr.pts_2d = d.pts_2d + b * 2 * d.n_pts;
@@ -60,15 +49,64 @@ __global__ void __launch_bounds__(NT, 1) solve_fused_kernel(cvxpnpl_b200_desc d,
     pr.line_3d = d.line_3d + b * 6 * d.n_lines;
     pr.n_pts = d.n_pts;
     pr.n_lines = d.n_lines;
+    return pr;
+}
 
-    cvx::Result rs;
-    cvx::solve_problem(pr, o, V, M, QR, d.R + b * 36, d.t + b * 12, d.Z ? d.Z + b * 100 : nullptr, rs);
-    d.n_poses[b] = rs.n_poses;
-    d.status[b] = rs.status;
-    d.iters[b] = rs.iters;
-    if (d.obj) {
-        d.obj[2 * b] = rs.pobj;
-        d.obj[2 * b + 1] = rs.dobj;
+// ---------------------------------------------------------------------------------
+// Fused persistent kernel: assembly -> SDP -> extraction.  One CTA per SM, one
+// problem per thread at a time; a finished lane immediately pulls the next problem
+// index from `counter` (lane-level work stealing), so the iteration-count spread
+// of the batch (median ~300, tail to 2500) costs no idle lanes.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1)
+solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, int64_t ws_stride)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t slot = (int64_t)blockIdx.x * NT + tid;
+
+    cvx::Arr<NT> V{smem + tid};
+    cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
+    cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
+    cvx::Arr<NT> L{smem + (size_t)210 * NT + tid};
+    cvx::GArr QR{d.workspace + slot, ws_stride};
+
+    int64_t b = -1;
+    bool exhausted = false;
+    cvx::LaneState st;
+    st.finite = false;
+    st.iterating = false;
+    st.converged = false;
+    st.it = 0;
+    st.phase = 0;
+    st.rho = 0.0;
+    st.dobj = 0.0;
+    for (;;) {
+        if (b < 0 && !exhausted) {
+            const unsigned long long nb = atomicAdd(counter, 1ULL);
+            if (nb < (unsigned long long)d.batch) {
+                b = (int64_t)nb;
+                cvx::problem_begin(problem_at(d, b), o, V, M, L, QR, st);
+            } else {
+                exhausted = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, b < 0)) break;   // queue empty and every lane idle
+        if (b >= 0) {
+            if (cvx::problem_pass(o, V, M, T, L, QR, st)) {
+                cvx::Result rs;
+                cvx::problem_finish(problem_at(d, b), o, V, M, T, L, QR, st, d.R + b * 36, d.t + b * 12,
+                                    d.Z ? d.Z + b * 100 : nullptr, rs);
+                d.n_poses[b] = rs.n_poses;
+                d.status[b] = rs.status;
+                d.iters[b] = rs.iters;
+                if (d.obj) {
+                    d.obj[2 * b] = rs.pobj;
+                    d.obj[2 * b + 1] = rs.dobj;
+                }
+                b = -1;
+            }
+        }
     }
 }
 
@@ -89,7 +127,7 @@ __global__ void assemble_kernel(cvxpnpl_b200_desc d, double* Q, double* Bmat)
 }
 
 __global__ void __launch_bounds__(NT, 1)
-solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q)
+solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
@@ -97,29 +135,42 @@ solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q)
     if (b >= d.batch) return;
     cvx::Arr<NT> V{smem + tid};
     cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
-    cvx::Arr<NT> qr{smem + (size_t)155 * NT + tid};
+    cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
+    cvx::Arr<NT> L{smem + (size_t)210 * NT + tid};
+    cvx::GArr qr{d.workspace + b, ws_stride};
     const double* Qi = Q + b * 81;
     double nq = 0;
     for (int i = 0; i < 9; ++i)
         for (int j = 0; j < 9; ++j) nq = fma(Qi[9 * i + j], Qi[9 * i + j], nq);
-    const double rho = o.rho_rel * sqrt(nq);
-    const bool finite = (rho > 0.0) && isfinite(rho);
+    cvx::LaneState st;
+    st.rho = o.rho_rel * sqrt(nq);
+    st.finite = (st.rho > 0.0) && isfinite(st.rho);
+    st.iterating = st.finite;
+    st.converged = false;
+    st.it = 0;
+    st.phase = 0;
+    st.dobj = 0.0;
     for (int i = 0; i < 9; ++i)
-        for (int j = 0; j <= i; ++j) qr[cvx::sidx(i, j)] = 0.5 * (Qi[9 * i + j] + Qi[9 * j + i]) / rho;
+        for (int j = 0; j <= i; ++j) qr[cvx::sidx(i, j)] = 0.5 * (Qi[9 * i + j] + Qi[9 * j + i]) / st.rho;
+    for (int i = 0; i < 10; ++i) {
+        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
+        for (int j = 0; j <= i; ++j) M[cvx::sidx(i, j)] = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
+        L[i] = (i == 9) ? o.sigma * o.sigma : 1.0 / 3.0;
+    }
+    for (int guard = 0; guard < o.max_iters + 40; ++guard)
+        if (cvx::problem_pass(o, V, M, T, L, qr, st)) break;
     double lam[10];
-    bool converged = false;
-    int it = 0;
+    for (int j = 0; j < 10; ++j) lam[j] = L[j];
     int32_t status = cvx::ST_NAN;
-    if (finite) {
-        it = cvx::dr_solve(V, M, qr, o, lam, converged);
-        status = converged ? cvx::ST_OK : cvx::ST_MAX_ITERS;
+    if (st.finite) {
+        status = st.converged ? cvx::ST_OK : cvx::ST_MAX_ITERS;
         for (int j = 0; j < 10; ++j)
             if (!isfinite(lam[j])) status = cvx::ST_NAN;
     }
-    const double dobj = (status != cvx::ST_NAN) ? cvx::dual_objective(V, lam, qr, rho) : nan("");
+    const double dobj = (status != cvx::ST_NAN) ? st.dobj : nan("");
     if (d.Z) cvx::write_Z(V, lam, status == cvx::ST_NAN, d.Z + b * 100);
     if (d.status) d.status[b] = status;
-    if (d.iters) d.iters[b] = it;
+    if (d.iters) d.iters[b] = st.it;
     if (d.obj) {
         d.obj[2 * b] = nan("");
         d.obj[2 * b + 1] = dobj;
@@ -191,12 +242,17 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     Opts o;
     const double eps = d->eps > 0 ? d->eps : 1e-9;
     o.eps2 = eps * eps;
-    o.alpha = d->alpha > 0 ? d->alpha : 1.0;
-    o.rho_rel = d->rho_rel > 0 ? d->rho_rel : 0.02;
+    o.alpha = d->alpha > 0 ? d->alpha : 1.3;
+    o.rho_rel = d->rho_rel > 0 ? d->rho_rel : 0.01;
+    o.sigma = d->sigma > 0 ? d->sigma : 1.5;
     o.max_iters = d->max_iters > 0 ? d->max_iters : 2500;
     o.sweeps = d->sweeps > 0 ? d->sweeps : 1;
     return o;
 }
+
+int64_t ws_stride_for(int64_t batch) { return ((batch + NT - 1) / NT) * NT; }
+constexpr int64_t PERSISTENT_SLOTS = 1024 * NT;   // >= (#SMs of any device) * NT
+constexpr int64_t WS_HEADER_DOUBLES = 16;
 
 }  // namespace
 
@@ -208,10 +264,11 @@ int cvxpnpl_b200_last_launch_count(void) { return g_launches; }
 
 size_t cvxpnpl_b200_workspace_bytes(int64_t batch)
 {
-    // all per-problem state lives in shared memory and registers; the entry is
-    // kept so callers are ready for variants that need device scratch
-    (void)batch;
-    return 0;
+    if (batch <= 0) return 0;
+    // work counter (header) + Q/rho scratch [45][slots]; slots = padded batch for the
+    // stage kernel, at most PERSISTENT_SLOTS thread slots for the persistent one
+    const int64_t slots = ws_stride_for(batch) > PERSISTENT_SLOTS ? ws_stride_for(batch) : PERSISTENT_SLOTS;
+    return ((size_t)slots * 45 + WS_HEADER_DOUBLES) * sizeof(double);
 }
 
 int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
@@ -233,8 +290,22 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int64_t blocks = (d->batch + NT - 1) / NT;
-    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d));
+    int dev = 0, n_sm = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
+    // persistent grid: one CTA per SM (shared memory allows exactly one), never more
+    // CTAs than there is work for
+    const int64_t want = (d->batch + NT - 1) / NT;
+    const int64_t blocks = want < n_sm ? want : n_sm;
+    // the work counter lives in front of the Q/rho scratch
+    unsigned long long* counter = (unsigned long long*)d->workspace;
+    cvxpnpl_b200_desc dd = *d;
+    dd.workspace = d->workspace + WS_HEADER_DOUBLES;
+    e0 = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+    if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
+    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter,
+                                                                                  PERSISTENT_SLOTS);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
@@ -273,7 +344,10 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
         attr_set = true;
     }
     const int64_t blocks = (d->batch + NT - 1) / NT;
-    solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(*d, make_opts(d), Q);
+    cvxpnpl_b200_desc dd = *d;
+    dd.workspace = d->workspace + WS_HEADER_DOUBLES;
+    solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), Q,
+                                                                                ws_stride_for(d->batch));
     g_launches = 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));

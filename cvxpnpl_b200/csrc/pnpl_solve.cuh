@@ -14,6 +14,7 @@ struct Opts {
     double rho_rel;   // penalty relative to ||Q||_F
     int max_iters;
     int sweeps;       // Jacobi sweeps per iteration (warm started)
+    double sigma;     // homogeneous-coordinate scaling (see dr_step)
 };
 
 struct Problem {
@@ -34,60 +35,150 @@ struct Result {
 // DR/ADMM loop for one problem.  On entry qr holds Q/rho.  On exit V, lam hold a
 // converged eigen-decomposition of the final DR iterate M (Z = V max(lam,0) V').
 // ---------------------------------------------------------------------------------
-template <int S, class QR>
-CVX_HD int dr_solve(Arr<S> V, Arr<S> M, QR qr, const Opts& o, double lam[10], bool& converged)
+// ---------------------------------------------------------------------------------
+// Per-problem state machine.  The CUDA kernel is persistent: every lane pulls the
+// next problem from a global counter as soon as its current one is finished, so
+// no lane waits for the slowest problem of its warp / CTA (iteration counts vary
+// from ~250 to 2500).  The three phases:
+//     problem_begin   assembly, rho, Q/rho, start point
+//     problem_pass    one DR iteration + warm-started Jacobi sweep (or, once the DR
+//                     loop has stopped, one more pass that polishes the
+//                     eigen-decomposition); returns true when the problem is done
+//     problem_finish  dual objective, optional Z, pose extraction
+// V (100), M (55), T (55), L (10) are the problem's strided work arrays (220
+// doubles, shared memory in the CUDA kernel); QR (45, Q/rho) is a strided scratch
+// that may live in global memory.
+// ---------------------------------------------------------------------------------
+struct LaneState {
+    double rho, dobj;
+    int32_t it;
+    // phase 0: DR iterations; 1: polishing the eigen-decomposition of the last
+    // (scaled) iterate; 2: eigen-decomposition of the unscaled Z (only when sigma != 1
+    // and the solution may have rank > 1)
+    int32_t phase;
+    bool finite, iterating, converged;
+};
+
+template <int S, class QRT>
+CVX_HD void problem_begin(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
 {
+    // Q (45) and B (27) land in the V region, which is free until it is initialised
+    Arr<S> Qs = V;
+    Arr<S> Bs = V.sub(45);
+    bool finite = assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
+    double nq = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const double q = Qs[sidx(i, j)];
+            nq = fma((i == j) ? 1.0 : 2.0, q * q, nq);
+        }
+    const double rho = o.rho_rel * sqrt(nq);
+    finite = finite && (rho > 0.0) && isfinite(rho);
+    const double ir = 1.0 / rho;
+#pragma unroll
+    for (int e = 0; e < 45; ++e) QR[e] = Qs[e] * ir;
     // start: Z0 = blkdiag(I/3, 1) (feasible for the diagonal block), U0 = 0
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
 #pragma unroll
         for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
 #pragma unroll
-        for (int j = 0; j <= i; ++j) M[sidx(i, j)] = (i == j) ? (i == 9 ? 1.0 : 1.0 / 3.0) : 0.0;
-        lam[i] = (i == 9) ? 1.0 : 1.0 / 3.0;
+        for (int j = 0; j <= i; ++j) M[sidx(i, j)] = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
+        L[i] = (i == 9) ? o.sigma * o.sigma : 1.0 / 3.0;
     }
-    converged = false;
-    int it = 0;
-    bool iterating = true;
-    // One loop body serves both the DR iterations (one warm-started sweep each) and
-    // the final passes that drive the eigen-decomposition of the last iterate to
-    // full convergence, so the (large, unrolled) sweep code exists once.
-    for (int guard = 0; guard < o.max_iters + 40; ++guard) {
-        if (iterating) {
-            double z[55];
-            const double res = dr_step(M, V, lam, qr, o.alpha, z);
-            ++it;
-            if (!(res > o.eps2)) {  // also leaves on NaN
-                converged = (res <= o.eps2);
-                iterating = false;
-            } else if (it >= o.max_iters) {
-                iterating = false;
-            }
+    st.rho = rho;
+    st.dobj = 0.0;
+    st.phase = 0;
+    st.it = 0;
+    st.finite = finite;
+    st.iterating = finite;
+    st.converged = false;
+}
+
+// One loop body serves both the DR iterations (one warm-started sweep each) and the
+// final passes that drive the eigen-decomposition of the last iterate to full
+// convergence, so the sweep code exists once.  Returns true when done.
+template <int S, class QR>
+CVX_HD double dual_objective(Arr<S> V, Arr<S> L, QR qr, double rho, double sigma);
+
+template <int S, class QRT>
+CVX_HD bool problem_pass(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR, LaneState& st)
+{
+    if (!st.finite) return true;
+    if (st.iterating) {
+        double z[55];
+        const double res = dr_step(M, V, L, QR, o.alpha, 1.0 / o.sigma, z);
+        ++st.it;
+        if (!(res > o.eps2)) {  // also leaves on NaN
+            st.converged = (res <= o.eps2);
+            st.iterating = false;
+            st.phase = 1;
+        } else if (st.it >= o.max_iters) {
+            st.iterating = false;
+            st.phase = 1;
         }
-        double t[55];
-        rotate_into_basis_reg(M, V, t);
-        double off = 0.0, dg = 0.0;
-        for (int s = 0; s < (iterating ? o.sweeps : 1); ++s) off = jacobi_sweep_reg(t, V);
+    }
+    rotate_into_basis(M, V, T);
+    double t[55];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
-            lam[j] = t[sidx(j, j)];
-            dg = fma(lam[j], lam[j], dg);
-        }
-        if (!iterating && !(off > 1e-22 * dg)) break;
+    for (int e = 0; e < 55; ++e) t[e] = T[e];
+    double off = 0.0, dg = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < (st.iterating ? o.sweeps : 1); ++s) off = jacobi_sweep_reg(t, V);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const double l = t[sidx(j, j)];
+        L[j] = l;
+        dg = fma(l, l, dg);
     }
-    return it;
+    if (st.iterating) return false;
+    if (!isfinite(dg)) return true;  // NaN-safe: a non-finite iterate ends the problem
+    if (off > 1e-22 * dg) return false;
+    if (st.phase == 2) return true;
+    // phase 1 finished: V, L is the eigen-decomposition of the scaled iterate M'
+    st.dobj = dual_objective(V, L, QR, st.rho, o.sigma);
+    if (o.sigma == 1.0) return true;
+    int above = 0;
+#pragma unroll 1
+    for (int j = 0; j < 10; ++j) above += (L[j] > 1e-3) ? 1 : 0;
+    const double isig = 1.0 / o.sigma;
+    if (above <= 1) {
+        // rank <= 1 for certain (eigenvalues of Z lie in [lam'/sigma^2, lam']): the
+        // eigenvector of Z is D^-1 v'; un-scaling row 9 of V is all extraction needs
+#pragma unroll
+        for (int j = 0; j < 10; ++j) V[90 + j] = V[90 + j] * isig;
+        return true;
+    }
+    // possible rank > 1: the reference thresholds the eigenvalues of the UNSCALED Z
+    // (cvxpnpl.py:499-502), so decompose Z = D^-1 P_psd(M') D^-1 itself; the passes
+    // run in this same loop (M is free now)
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r)
+#pragma unroll 1
+        for (int c = 0; c <= r; ++c) {
+            double s = 0;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) s = fma(fmax(L[j], 0.0) * V[r * 10 + j], V[c * 10 + j], s);
+            if (r == 9) s *= isig;
+            if (c == 9) s *= isig;
+            M[sidx(r, c)] = s;
+        }
+    st.phase = 2;
+    return false;
 }
 
 // Dual objective.  At the fixed point Q + rho U = sum_k y_k P_k with U = V min(lam,0) V'
 // the scaled dual slack, so for ANY affine-feasible point Zf the dual objective
-// y_0 = sum_k y_k <P_k, Zf> = <Q + rho U, Zf>.  Zf = blkdiag(I/3, 1) is used.
+// y_0 = sum_k y_k <P_k, Zf> = <Q + rho U, Zf>.  Zf = blkdiag(I/3, sigma^2) is used.
 template <int S, class QR>
-CVX_HD double dual_objective(Arr<S> V, const double lam[10], QR qr, double rho)
+CVX_HD double dual_objective(Arr<S> V, Arr<S> L, QR qr, double rho, double sigma)
 {
     double tr9 = 0, u99 = 0, tq = 0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 10; ++j) {
-        const double ln = fmin(lam[j], 0.0);
+        const double ln = fmin(L[j], 0.0);
         double s = 0;
 #pragma unroll
         for (int i = 0; i < 9; ++i) s = fma(V[i * 10 + j], V[i * 10 + j], s);
@@ -96,7 +187,8 @@ CVX_HD double dual_objective(Arr<S> V, const double lam[10], QR qr, double rho)
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) tq += qr[sidx(i, i)];
-    return rho * ((tq + tr9) * (1.0 / 3.0) + u99);
+    // feasible point of the scaled problem: blkdiag(I/3, sigma^2)
+    return rho * ((tq + tr9) * (1.0 / 3.0) + sigma * sigma * u99);
 }
 
 template <int S>
@@ -113,59 +205,45 @@ CVX_HD void write_Z(Arr<S> V, const double lam[10], bool is_nan, double* Zo)
         }
 }
 
-// Whole path for one problem.  V (100), M (55) and QR (45) are the problem's strided
-// work arrays (200 doubles per problem, all in shared memory in the CUDA kernel).
-template <int S>
-CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> QR,
-                          double* R_out, double* t_out, double* Z_out, Result& rs)
+template <int S, class QRT>
+CVX_HD void problem_finish(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR,
+                           const LaneState& st, double* R_out, double* t_out, double* Z_out, Result& rs)
 {
-    // ---- assembly: Q (45) and B (27) land in the V region, which is free until the
-    // DR loop initialises it; Q/rho goes to its own region ---------------------------
-    double rho;
-    bool finite;
-    {
-        Arr<S> Qs = V;
-        Arr<S> Bs = V.sub(45);
-        finite = assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
-        double nq = 0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                const double q = Qs[sidx(i, j)];
-                nq = fma((i == j) ? 1.0 : 2.0, q * q, nq);
-            }
-        rho = o.rho_rel * sqrt(nq);
-        finite = finite && (rho > 0.0) && isfinite(rho);
-        const double ir = 1.0 / rho;
-#pragma unroll
-        for (int e = 0; e < 45; ++e) QR[e] = Qs[e] * ir;
-    }
-
-    int32_t status = ST_NAN;
-    int it = 0;
     double lam[10];
-    bool converged = false;
-    if (finite) {
-        it = dr_solve(V, M, QR, o, lam, converged);
-        status = converged ? ST_OK : ST_MAX_ITERS;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) lam[j] = L[j];
+    int32_t status = ST_NAN;
+    if (st.finite) {
+        status = st.converged ? ST_OK : ST_MAX_ITERS;
 #pragma unroll
         for (int j = 0; j < 10; ++j)
             if (!isfinite(lam[j])) status = ST_NAN;
     }
-    const double dobj = (status != ST_NAN) ? dual_objective(V, lam, QR, rho) : nan("");
+    const double dobj = (status != ST_NAN) ? st.dobj : nan("");
     if (Z_out) write_Z(V, lam, status == ST_NAN, Z_out);
-
-    // ---- extraction: Q and B are re-assembled (cheap) into the now free M / QR regions
+    // Q and B are re-assembled (cheap) into the now free M / T regions
     Arr<S> Qs = M;
-    Arr<S> Bs = QR;
+    Arr<S> Bs = T;
     if (status != ST_NAN) assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
     double pobj;
     rs.n_poses = extract_poses(V, lam, Qs, Bs, status, dobj, sqrt(o.eps2), R_out, t_out, pobj);
     rs.status = status;
-    rs.iters = it;
+    rs.iters = st.it;
     rs.pobj = pobj;
     rs.dobj = dobj;
+}
+
+// The whole path for one problem, sequentially (host harness, stage kernels).
+template <int S, class QRT>
+CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR,
+                          double* R_out, double* t_out, double* Z_out, Result& rs)
+{
+    LaneState st;
+    problem_begin(pr, o, V, M, L, QR, st);
+#pragma unroll 1
+    for (int guard = 0; guard < o.max_iters + 40; ++guard)
+        if (problem_pass(o, V, M, T, L, QR, st)) break;
+    problem_finish(pr, o, V, M, T, L, QR, st, R_out, t_out, Z_out, rs);
 }
 
 }  // namespace cvx

@@ -64,6 +64,7 @@ typedef struct cvxpnpl_b200_desc {
     int32_t sweeps;         /* Jacobi sweeps per ADMM iteration (warm started); 0 = default */
     double rho_rel;         /* ADMM penalty = rho_rel * ||Q||_F ; 0 = default */
     double alpha;           /* over-relaxation in (0,2); 0 = default */
+    double sigma;           /* homogeneous-coordinate scaling (preconditioner); 0 = default */
     /* ---- outputs ---- */
     double* R;              /* [B, 4, 3, 3] world->camera rotations, NaN padded */
     double* t;              /* [B, 4, 3] */

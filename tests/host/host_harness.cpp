@@ -13,16 +13,17 @@
 extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
                           const double* pts_2d, const double* pts_3d, const double* line_2d,
                           const double* line_3d, double eps, int max_iters, int sweeps, double rho_rel,
-                          double alpha, double* R, double* t, int32_t* n_poses, int32_t* status,
+                          double alpha, double sigma, double* R, double* t, int32_t* n_poses, int32_t* status,
                           int32_t* iters, double* obj, double* Z)
 {
     cvx::Opts o;
     o.eps2 = eps * eps;
-    o.alpha = alpha > 0 ? alpha : 1.0;
-    o.rho_rel = rho_rel > 0 ? rho_rel : 0.02;
+    o.alpha = alpha > 0 ? alpha : 1.3;
+    o.rho_rel = rho_rel > 0 ? rho_rel : 0.01;
     o.max_iters = max_iters > 0 ? max_iters : 2500;
     o.sweeps = sweeps > 0 ? sweeps : 1;
-    std::vector<double> V(100), M(55), qr(45);
+    o.sigma = sigma > 0 ? sigma : 1.5;
+    std::vector<double> V(100), M(55), T(55), L(10), qr(45);
     for (int64_t b = 0; b < B; ++b) {
         cvx::Problem pr;
         pr.K = k_batched ? K + 9 * b : K;
@@ -33,7 +34,8 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
         pr.n_pts = n_pts;
         pr.n_lines = n_lines;
         cvx::Result rs;
-        cvx::solve_problem(pr, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{M.data()}, cvx::Arr<1>{qr.data()},
+        cvx::solve_problem(pr, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{M.data()}, cvx::Arr<1>{T.data()},
+                           cvx::Arr<1>{L.data()}, cvx::Arr<1>{qr.data()},
                            R + b * 36, t + b * 12, Z ? Z + b * 100 : nullptr, rs);
         n_poses[b] = rs.n_poses;
         status[b] = rs.status;
