@@ -254,17 +254,35 @@ CVX_HD constexpr int jp_p(int k) { return k; }          // fixed pairs (k, 9-k),
 CVX_HD constexpr int jp_q(int k) { return 9 - k; }
 CVX_HD constexpr int jp_sigma(int i) { return i == 0 ? 0 : (i == 9 ? 1 : i + 1); }
 
-// rotation angle for pivot (p,q)
+// reciprocal square root: device intrinsic path / host libm
+CVX_HD double cvx_rsqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// Rotation for pivot (p,q) annihilating a_pq (classical Jacobi, |angle| <= pi/4):
+//   d = a_qq - a_pp, b = 2 a_pq, h = sqrt(d^2 + b^2)
+//   cos^2 = (h + |d|) / (2h),  sin = sgn(d) b / (2 h cos),  tan = sin / cos
+// written with two reciprocal square roots and no division, which keeps the
+// dependent chain short (the five chains of a round are the critical path).
 CVX_HD void jacobi_cs(double app, double aqq, double apq, double& c, double& s, double& tn)
 {
     const double d = aqq - app, b2 = 2.0 * apq;
-    const double h = sqrt(fma(d, d, b2 * b2));
-    const double den = fabs(d) + h;
-    // negligible pivot (also covers d = b2 = 0): identity rotation
-    const bool skip = !(fabs(apq) > 1e-18 * den) || !(den > 1e-300);
-    tn = skip ? 0.0 : copysign(1.0, d) * b2 / den;
-    c = 1.0 / sqrt(fma(tn, tn, 1.0));
-    s = tn * c;
+    const double g = fma(d, d, b2 * b2);
+    const double ad = fabs(d);
+    // negligible pivot (also covers d = b2 = 0 and underflow of g): identity rotation
+    const bool skip = !(fabs(apq) > 1e-18 * ad) || !(g > 1e-280);
+    const double ig = cvx_rsqrt(skip ? 1.0 : g);
+    const double c2 = fma(0.5 * ad, ig, 0.5);          // in [0.5, 1]
+    const double rc = cvx_rsqrt(c2);
+    const double sg = copysign(0.5, d) * b2 * ig;       // sin * cos
+    c = skip ? 1.0 : c2 * rc;
+    s = skip ? 0.0 : sg * rc;
+    tn = skip ? 0.0 : sg * rc * rc;
 }
 
 // one sweep; returns the off-diagonal square sum seen at the pivots (before they
@@ -309,21 +327,29 @@ CVX_HD double jacobi_sweep_reg(double t[55], Arr<S> V)
 #pragma unroll
             for (int e = 0; e < 55; ++e) t[e] = u[e];
         }
-        // rotate + permute the columns of V, one row at a time
+        // rotate + permute the columns of V, two rows at a time (two independent
+        // instruction streams for the single resident warp of the scheduler)
 #pragma unroll 1
-        for (int row = 0; row < 10; ++row) {
-            double v[10];
+        for (int row = 0; row < 10; row += 2) {
+            double v[2][10];
 #pragma unroll
-            for (int j = 0; j < 10; ++j) v[j] = V[row * 10 + j];
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 10; ++j) v[h][j] = V[(row + h) * 10 + j];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const int p = jp_p(k), q = jp_q(k);
-                const double vp = v[p], vq = v[q];
-                v[p] = fma(cs[k], vp, -sn[k] * vq);
-                v[q] = fma(sn[k], vp, cs[k] * vq);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double vp = v[h][p], vq = v[h][q];
+                    v[h][p] = fma(cs[k], vp, -sn[k] * vq);
+                    v[h][q] = fma(sn[k], vp, cs[k] * vq);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 10; ++j) V[row * 10 + jp_sigma(j)] = v[j];
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 10; ++j) V[(row + h) * 10 + jp_sigma(j)] = v[h][j];
         }
     }
     return off;
@@ -360,20 +386,25 @@ CVX_HD void rotate_into_basis(Arr<S> M, Arr<S> V, Arr<S> T)
                     }
                 }
         }
+        // rows i = j0 .. 9 in pairs (j0 is even, so the count is even): four
+        // independent dot-product chains
 #pragma unroll 1
-        for (int i = j0; i < 10; ++i) {
-            double s0 = 0.0, s1 = 0.0;
+        for (int i = j0; i < 10; i += 2) {
+            double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
 #pragma unroll
             for (int k = 0; k < 10; ++k) {
-                const double vik = V[k * 10 + i];
-                s0 = fma(vik, w0[k], s0);
-                s1 = fma(vik, w1[k], s1);
+                const double va = V[k * 10 + i], vb = V[k * 10 + i + 1];
+                s00 = fma(va, w0[k], s00);
+                s01 = fma(va, w1[k], s01);
+                s10 = fma(vb, w0[k], s10);
+                s11 = fma(vb, w1[k], s11);
             }
-            const int base = (i * (i + 1)) / 2 + j0;
-            T[base] = s0;
-            // (i, j0+1): for i == j0 this is the transposed duplicate of (j0+1, j0),
-            // which the next i writes as well -- skip it
-            if (i > j0) T[base + 1] = s1;
+            const int ba = (i * (i + 1)) / 2 + j0, bb = ((i + 1) * (i + 2)) / 2 + j0;
+            T[ba] = s00;
+            // (i, j0+1) with i == j0 is the transposed duplicate of (j0+1, j0): skip
+            if (i > j0) T[ba + 1] = s01;
+            T[bb] = s10;
+            T[bb + 1] = s11;
         }
     }
 }
