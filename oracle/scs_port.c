@@ -10,7 +10,8 @@
  * on the homogeneous self-dual embedding with over-relaxation, a cached
  * factorisation of the (data independent) linear system, and Euclidean
  * projection onto  {0}^22 x S_+^10  in SCS's svec (sqrt(2) off-diagonal)
- * coordinates.  SCS's data equilibration and Anderson acceleration are NOT
+ * coordinates (eigen-decomposition by Householder tridiagonalisation + implicit
+ * QL, the dsyev algorithm SCS obtains from LAPACK).  SCS's data equilibration and Anderson acceleration are NOT
  * restated: they change the trajectory, not the fixed point.
  *
  * PARITY UNPINNED at the SCS boundary: the reference holds no golden vectors
@@ -128,42 +129,111 @@ static void solveM(const double *wx, const double *wy, double *x, double *y)
     for (int k = 0; k < M_; ++k) y[k] += wy[k];
 }
 
-/* cyclic Jacobi symmetric eigensolver, cold start, PS x PS */
-static void jacobi_eig(double *S, double *V)
+/* Symmetric eigen-decomposition, PS x PS: Householder tridiagonalisation followed
+ * by implicit-shift QL (the algorithm behind LAPACK dsteqr/dsyev, which SCS calls
+ * for its PSD projections).  On exit the columns of Z are the eigenvectors and
+ * d[] the eigenvalues.  Z holds the symmetric input on entry. */
+static void sym_eig(double *Z, double *d)
 {
-    for (int i = 0; i < PS; ++i)
-        for (int j = 0; j < PS; ++j) V[i * PS + j] = (i == j);
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        double off = 0, dg = 0;
-        for (int i = 0; i < PS; ++i)
-            for (int j = 0; j < PS; ++j)
-                if (i != j) off += S[i * PS + j] * S[i * PS + j];
-                else dg += S[i * PS + j] * S[i * PS + j];
-        if (off <= 1e-34 * (dg + off) || off == 0.0) break;
-        for (int p = 0; p < PS - 1; ++p)
-            for (int q = p + 1; q < PS; ++q) {
-                double apq = S[p * PS + q];
-                /* negligible pivot: skip (also keeps denormals out of the loop) */
-                if (fabs(apq) <= 1e-20 * (fabs(S[p * PS + p]) + fabs(S[q * PS + q])) || fabs(apq) < 1e-290) continue;
-                double theta = (S[q * PS + q] - S[p * PS + p]) / (2 * apq);
-                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-                double c = 1 / sqrt(t * t + 1), s = t * c;
-                for (int k = 0; k < PS; ++k) {
-                    double akp = S[k * PS + p], akq = S[k * PS + q];
-                    S[k * PS + p] = c * akp - s * akq;
-                    S[k * PS + q] = s * akp + c * akq;
+    const int n = PS;
+    double e[PS];
+    /* --- Householder reduction to tridiagonal form (accumulating transforms) --- */
+    for (int i = n - 1; i > 0; --i) {
+        const int l = i - 1;
+        double h = 0.0, scale = 0.0;
+        if (l > 0) {
+            for (int k = 0; k <= l; ++k) scale += fabs(Z[i * n + k]);
+            if (scale == 0.0) {
+                e[i] = Z[i * n + l];
+            } else {
+                for (int k = 0; k <= l; ++k) {
+                    Z[i * n + k] /= scale;
+                    h += Z[i * n + k] * Z[i * n + k];
                 }
-                for (int k = 0; k < PS; ++k) {
-                    double apk = S[p * PS + k], aqk = S[q * PS + k];
-                    S[p * PS + k] = c * apk - s * aqk;
-                    S[q * PS + k] = s * apk + c * aqk;
+                double f = Z[i * n + l];
+                double g = (f >= 0.0) ? -sqrt(h) : sqrt(h);
+                e[i] = scale * g;
+                h -= f * g;
+                Z[i * n + l] = f - g;
+                f = 0.0;
+                for (int j = 0; j <= l; ++j) {
+                    Z[j * n + i] = Z[i * n + j] / h;
+                    g = 0.0;
+                    for (int k = 0; k <= j; ++k) g += Z[j * n + k] * Z[i * n + k];
+                    for (int k = j + 1; k <= l; ++k) g += Z[k * n + j] * Z[i * n + k];
+                    e[j] = g / h;
+                    f += e[j] * Z[i * n + j];
                 }
-                for (int k = 0; k < PS; ++k) {
-                    double vkp = V[k * PS + p], vkq = V[k * PS + q];
-                    V[k * PS + p] = c * vkp - s * vkq;
-                    V[k * PS + q] = s * vkp + c * vkq;
+                const double hh = f / (h + h);
+                for (int j = 0; j <= l; ++j) {
+                    f = Z[i * n + j];
+                    e[j] = g = e[j] - hh * f;
+                    for (int k = 0; k <= j; ++k) Z[j * n + k] -= (f * e[k] + g * Z[i * n + k]);
                 }
             }
+        } else {
+            e[i] = Z[i * n + l];
+        }
+        d[i] = h;
+    }
+    d[0] = 0.0;
+    e[0] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int l = i - 1;
+        if (d[i] != 0.0) {
+            for (int j = 0; j <= l; ++j) {
+                double g = 0.0;
+                for (int k = 0; k <= l; ++k) g += Z[i * n + k] * Z[k * n + j];
+                for (int k = 0; k <= l; ++k) Z[k * n + j] -= g * Z[k * n + i];
+            }
+        }
+        d[i] = Z[i * n + i];
+        Z[i * n + i] = 1.0;
+        for (int j = 0; j <= l; ++j) Z[j * n + i] = Z[i * n + j] = 0.0;
+    }
+    /* --- implicit QL on the tridiagonal matrix ---------------------------------- */
+    for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    for (int l = 0; l < n; ++l) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; ++m) {
+                const double dd = fabs(d[m]) + fabs(d[m + 1]);
+                if (fabs(e[m]) <= 2.3e-16 * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 60) break;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? fabs(r) : -fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; --i) {
+                    double f = s * e[i], b = c * e[i];
+                    e[i + 1] = (r = hypot(f, g));
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0.0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    d[i + 1] = g + (p = s * r);
+                    g = c * r - b;
+                    for (int k = 0; k < n; ++k) {
+                        f = Z[k * n + i + 1];
+                        Z[k * n + i + 1] = s * Z[k * n + i] + c * f;
+                        Z[k * n + i] = c * Z[k * n + i] - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0.0;
+            }
+        } while (m != l);
     }
 }
 
@@ -180,9 +250,10 @@ static void proj_psd_svec(double *v)
             S[i * PS + j] = e;
             S[j * PS + i] = e;
         }
-    jacobi_eig(S, V);
     double lam[PS];
-    for (int i = 0; i < PS; ++i) lam[i] = S[i * PS + i] > 0 ? S[i * PS + i] : 0.0;
+    memcpy(V, S, sizeof(V));
+    sym_eig(V, lam);
+    for (int i = 0; i < PS; ++i) lam[i] = lam[i] > 0 ? lam[i] : 0.0;
     k = 0;
     for (int j = 0; j < PS; ++j)
         for (int i = j; i < PS; ++i, ++k) {
