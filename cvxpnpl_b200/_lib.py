@@ -55,6 +55,7 @@ EXPORTS = (
     "cvxpnpl_b200_solve_sdp",
     "cvxpnpl_b200_extract",
     "cvxpnpl_b200_last_launch_count",
+    "cvxpnpl_b200_fp64_probe",
 )
 
 _lib = None
@@ -89,6 +90,9 @@ def load():
     lib.cvxpnpl_b200_extract.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p]
     lib.cvxpnpl_b200_last_launch_count.restype = ctypes.c_int
+    lib.cvxpnpl_b200_fp64_probe.restype = ctypes.c_int
+    lib.cvxpnpl_b200_fp64_probe.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]
     _lib = lib
     return lib
 

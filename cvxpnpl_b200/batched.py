@@ -228,3 +228,26 @@ def extract_batched(Z, Q, Bmat, dobj=None, eps=1e-9) -> BatchedPoses:
     stream = torch.cuda.current_stream(device).cuda_stream
     _lib.check(lib.cvxpnpl_b200_extract(ctypes.byref(d), _ptr(Z), _ptr(Q), _ptr(Bmat), _ptr(dobj), ctypes.c_void_p(stream)))
     return out
+
+
+def measure_fp64_peak(device=None, iters=4000, repeats=5):
+    """Measured FP64 FMA throughput (TFLOP/s) of the device: best of `repeats`
+    launches of the library's probe kernel, timed with CUDA events."""
+    _require_cuda()
+    lib = _lib.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+        out = torch.empty(n_sm * 8 * 256, dtype=torch.float64, device=device)
+        flops = ctypes.c_int64(0)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        best = float("inf")
+        for _ in range(repeats + 1):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            _lib.check(lib.cvxpnpl_b200_fp64_probe(_ptr(out), out.numel(), int(iters), ctypes.byref(flops),
+                                                   ctypes.c_void_p(stream)))
+            e.record()
+            torch.cuda.synchronize(device)
+            best = min(best, s.elapsed_time(e))
+    return flops.value / (best * 1e-3) / 1e12

@@ -229,6 +229,23 @@ extract_kernel(cvxpnpl_b200_desc d, const double* Z, const double* Q, const doub
     }
 }
 
+// FP64 FMA throughput probe: 8 independent chains per thread, 256 threads per CTA,
+// 8 CTAs per SM.  Used by bench.py to measure the denominator of the fp64-pipe
+// fraction it reports next to the (tiny) HBM fraction.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 int check_common(const cvxpnpl_b200_desc* d)
 {
     if (!d) return fail(-1, "null descriptor");
@@ -307,6 +324,23 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter,
                                                                                   PERSISTENT_SLOTS);
     g_launches = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
+int cvxpnpl_b200_fp64_probe(double* out, int64_t out_len, int iters, int64_t* flops, void* stream)
+{
+    g_launches = 0;
+    int dev = 0, n_sm = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
+    const int blocks = n_sm * 8, threads = 256;
+    if (!out || out_len < (int64_t)blocks * threads) return fail(-7, "probe output too small");
+    fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-9);
+    g_launches = 1;
+    if (flops) *flops = (int64_t)blocks * threads * (int64_t)iters * 64 * 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     return 0;

@@ -105,6 +105,12 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* desc, const double* Q, void*
 int cvxpnpl_b200_extract(const cvxpnpl_b200_desc* desc, const double* Z, const double* Q,
                          const double* Bmat, const double* dobj, void* stream);
 
+/* Measurement aid (no reference counterpart): launches an FP64 FMA throughput
+ * probe; `out` needs (#SMs * 8 * 256) doubles, *flops receives the flop count of
+ * the launch.  bench.py times it with CUDA events to obtain the fp64 peak it
+ * quotes next to the HBM roofline. */
+int cvxpnpl_b200_fp64_probe(double* out, int64_t out_len, int iters, int64_t* flops, void* stream);
+
 /* Number of kernel launches issued by the last call on this host thread
  * (bench.py reports it as gpu_launches). */
 int cvxpnpl_b200_last_launch_count(void);

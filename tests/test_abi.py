@@ -12,7 +12,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 def test_exports_match_header():
     from cvxpnpl_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "cvxpnpl_b200.h")).read()
-    declared = set(re.findall(r"\b(cvxpnpl_b200_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(cvxpnpl_b200_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS)
     lib = _lib.load()
     for name in declared:

@@ -210,3 +210,68 @@ def test_extraction_degenerate(cb, golden, name):
         # see tests/test_oracle.py::test_degenerate_extraction for the tolerance
         assert dist[(n - 1) // 2] < 1e-6, (name, i, dist)
         assert np.all(dist[: max(n - 1, 1)] < 1e-4), (name, i, dist)
+
+
+@pytest.mark.parametrize("n_pts,n_lines,coplanar,min_found", [
+    (3, 0, False, 0.75), (4, 0, False, 0.95), (0, 3, False, 0.5), (2, 1, False, 0.6), (0, 4, False, 0.95),
+    (8, 0, True, 0.25)])
+def test_degenerate_sweep(cb, n_pts, n_lines, coplanar, min_found):
+    """BASELINE config 5 (minimal / planar configurations, rank > 1 SDP optima).  The
+    optimal face is not a point, so poses are not compared with the oracle's; checked
+    instead: status codes are legal, every finite candidate is orthonormal, and on
+    these NOISE-FREE problems the ground truth is among the candidates for at least
+    the fraction the reference's own extraction achieves (measured with the oracle;
+    its rank-2 averaging, cvxpnpl.py:303-315, degenerates to NaN on about half of the
+    planar cases)."""
+    from cvxpnpl_b200 import synth
+    B = 1700
+    d = synth.make_batch(B, n_pts, n_lines, noise=0.0, seed=9, coplanar=coplanar)
+    res = _solve(cb, d, n_pts, n_lines)
+    st = res.status.cpu().numpy() & 0xFF
+    n = res.n_poses.cpu().numpy()
+    assert np.isin(st, (0, 1, 3, 4)).all()
+    assert np.isin(n, (0, 1, 2, 4)).all()
+    R = res.R.cpu().numpy()
+    fin = np.isfinite(R).all(axis=(2, 3))
+    assert (fin.sum(1) <= n).all()
+    RtR = np.einsum("bkij,bklj->bkil", R, R)
+    assert np.abs(RtR[fin] - np.eye(3)).max() < 1e-9
+    ang = synth.rotation_angle(d["R_gt"][:, None], R)          # [B, 4]
+    ang = np.where(fin, ang, np.inf)
+    conv = st == 0
+    found = (ang.min(axis=1) < 1e-4)[conv].mean()
+    assert found >= min_found, found
+
+
+def test_full_size_pnp8_and_pnl6(cb):
+    """BASELINE configs 2 and 4 at reduced-but-large size through size-independent
+    properties (fp64 path): noise-free ground truth recovered wherever the solver
+    reports convergence with one pose, rotations orthonormal, duality gap closed."""
+    from cvxpnpl_b200 import synth
+    for n_pts, n_lines, B in ((8, 0, 100_000), (0, 6, 50_000)):
+        d = synth.make_batch(B, n_pts, n_lines, noise=0.0, seed=3)
+        res = _solve(cb, d, n_pts, n_lines)
+        st = (res.status & 0xFF).cpu().numpy()
+        n = res.n_poses.cpu().numpy()
+        ok = (st == 0) & (n == 1)
+        assert ok.mean() > (0.99 if n_pts else 0.85), ok.mean()
+        R, t = res.R[:, 0].cpu().numpy(), res.t[:, 0].cpu().numpy()
+        ang, terr = synth.pose_error(d["R_gt"], d["t_gt"], R, t)
+        assert np.nanmax(ang[ok]) < 1e-5 and np.nanmax(terr[ok]) < 1e-5, (np.nanmax(ang[ok]), np.nanmax(terr[ok]))
+        gap = (res.obj[:, 0] - res.obj[:, 1]).abs().cpu().numpy()
+        assert np.nanmax(gap[ok]) < 1e-7
+
+
+def test_stage_entry_points_compose(cb):
+    """assemble -> solve_sdp -> extract through the three stage entry points equals
+    the fused kernel."""
+    from cvxpnpl_b200 import synth
+    d = synth.make_batch(300, 8, 4, noise=1.0, seed=13)
+    fused = _solve(cb, d, 8, 4)
+    Q, Bm = cb.assemble_batched(d["K"], d["pts_2d"], d["pts_3d"], d["line_2d"], d["line_3d"])
+    Z, dobj, iters, status = cb.solve_sdp_batched(Q)
+    res = cb.extract_batched(Z, Q, Bm, dobj)
+    torch.cuda.synchronize()
+    assert torch.equal(iters, fused.iters)
+    assert float((res.R[:, 0] - fused.R[:, 0]).abs().max()) < 1e-9
+    assert float((res.t[:, 0] - fused.t[:, 0]).abs().max()) < 1e-9
