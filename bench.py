@@ -342,7 +342,7 @@ def run_ours(a):
             cores = host_cores()
             pool = make_pool(cores)
             r0, _ = cpu_rate(max(2 * cores, 16), n_pts, n_lines, a.noise, cores, pool)
-            sample = a.cpu_sample or max(cores, int(r0 * 15.0))  # about 15 s of CPU work
+            sample = a.cpu_sample or max(cores, int(r0 * 25.0))  # about 15-25 s of CPU work
             v, wall = cpu_rate(sample, n_pts, n_lines, a.noise, cores, pool)
             pool.close()
             line["cpu_baseline"] = {

@@ -523,59 +523,91 @@ CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, QR qr, double alpha, double 
 }
 
 // ---------------------------------------------------------------------------------
-// 3x3 orthogonal polar factor  U Vh  of a row-major 3x3 matrix (cvxpnpl.py:510-511,
-// SVD projection WITHOUT determinant correction).  Computed from the Jacobi
-// eigen-decomposition of A'A = W S^2 W':  U Vh = A W S^-1 W'.
+// 3x3 orthogonal factor  U Vh  of the SVD of a row-major 3x3 matrix (cvxpnpl.py:510-511,
+// SVD projection WITHOUT determinant correction).  One-sided (Hestenes) Jacobi:
+// rotate pairs of columns of A until they are orthogonal, A W = U S; then
+// U Vh = normalise_columns(A W) W'.  Always returns an orthogonal matrix, also for
+// the ill-conditioned candidates the multi-solution branch can produce (a column
+// with vanishing singular value is completed by a cross product, as any SVD would
+// complete it up to sign).
 // ---------------------------------------------------------------------------------
 CVX_HD void polar3(const double A[9], double R[9])
 {
-    double G[6];  // packed lower of A'A
+    double Bm[9], W[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j)
-            G[sym3(i, j)] = A[i] * A[j] + A[3 + i] * A[3 + j] + A[6 + i] * A[6 + j];
-    double W[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    for (int sweep = 0; sweep < 12; ++sweep) {
-        const double off = G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
-        if (off <= 1e-34 * (G[0] * G[0] + G[2] * G[2] + G[5] * G[5])) break;
+    for (int i = 0; i < 9; ++i) Bm[i] = A[i];
+    for (int sweep = 0; sweep < 20; ++sweep) {
+        double rot = 0.0;
 #pragma unroll
         for (int pq = 0; pq < 3; ++pq) {
-            const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2, k = 3 - p - q;
-            const double apq = G[sym3(q, p)];
-            if (apq == 0.0) continue;
-            const double app = G[sym3(p, p)], aqq = G[sym3(q, q)];
-            const double theta = (aqq - app) / (2.0 * apq);
-            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-            const double c = 1.0 / sqrt(fma(t, t, 1.0)), s = t * c;
-            G[sym3(p, p)] = app - t * apq;
-            G[sym3(q, q)] = aqq + t * apq;
-            G[sym3(q, p)] = 0.0;
-            const double akp = G[sym3(k, p)], akq = G[sym3(k, q)];
-            G[sym3(k, p)] = c * akp - s * akq;
-            G[sym3(k, q)] = s * akp + c * akq;
+            const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
+            const double al = Bm[p] * Bm[p] + Bm[3 + p] * Bm[3 + p] + Bm[6 + p] * Bm[6 + p];
+            const double be = Bm[q] * Bm[q] + Bm[3 + q] * Bm[3 + q] + Bm[6 + q] * Bm[6 + q];
+            const double ga = Bm[p] * Bm[q] + Bm[3 + p] * Bm[3 + q] + Bm[6 + p] * Bm[6 + q];
+            if (!(fabs(ga) > 1e-17 * sqrt(al * be)) || !(fabs(ga) > 1e-300)) continue;
+            rot += 1.0;
+            const double zeta = (be - al) / (2.0 * ga);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+            const double c = 1.0 / sqrt(fma(t, t, 1.0)), sn = c * t;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
+                const double bp = Bm[3 * r + p], bq = Bm[3 * r + q];
+                Bm[3 * r + p] = c * bp - sn * bq;
+                Bm[3 * r + q] = sn * bp + c * bq;
                 const double wp = W[3 * r + p], wq = W[3 * r + q];
-                W[3 * r + p] = c * wp - s * wq;
-                W[3 * r + q] = s * wp + c * wq;
+                W[3 * r + p] = c * wp - sn * wq;
+                W[3 * r + q] = sn * wp + c * wq;
             }
         }
+        if (rot == 0.0) break;
     }
-    // R = A * (W diag(1/sqrt(g)) W')
-    double is[3] = {1.0 / sqrt(G[0]), 1.0 / sqrt(G[2]), 1.0 / sqrt(G[5])};
-    double H[9];
+    double sv[3], smax = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        sv[j] = sqrt(Bm[j] * Bm[j] + Bm[3 + j] * Bm[3 + j] + Bm[6 + j] * Bm[6 + j]);
+        smax = fmax(smax, sv[j]);
+    }
+    bool good[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        good[j] = sv[j] > 1e-13 * smax && sv[j] > 0.0;
+        const double inv = good[j] ? 1.0 / sv[j] : 0.0;
+        Bm[j] *= inv; Bm[3 + j] *= inv; Bm[6 + j] *= inv;
+    }
+    // complete missing left singular vectors
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (good[j]) continue;
+        const int a = (j + 1) % 3, b = (j + 2) % 3;
+        if (!good[a] && !good[b]) {
+            // rank <= 1: pick any unit vector orthogonal to the remaining good one later
+            Bm[j] = (j == 0); Bm[3 + j] = (j == 1); Bm[6 + j] = (j == 2);
+            good[j] = true;
+            continue;
+        }
+        if (!good[a] || !good[b]) {
+            // one good column g: take the coordinate axis least aligned with it, orthogonalise
+            const int g = good[a] ? a : b;
+            const double gx = Bm[g], gy = Bm[3 + g], gz = Bm[6 + g];
+            double ex = 0, ey = 0, ez = 0;
+            if (fabs(gx) <= fabs(gy) && fabs(gx) <= fabs(gz)) ex = 1; else if (fabs(gy) <= fabs(gz)) ey = 1; else ez = 1;
+            const double dt = ex * gx + ey * gy + ez * gz;
+            double ux = ex - dt * gx, uy = ey - dt * gy, uz = ez - dt * gz;
+            const double nu = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
+            Bm[j] = ux * nu; Bm[3 + j] = uy * nu; Bm[6 + j] = uz * nu;
+            good[j] = true;
+            continue;
+        }
+        Bm[j] = Bm[3 + a] * Bm[6 + b] - Bm[6 + a] * Bm[3 + b];
+        Bm[3 + j] = Bm[6 + a] * Bm[b] - Bm[a] * Bm[6 + b];
+        Bm[6 + j] = Bm[a] * Bm[3 + b] - Bm[3 + a] * Bm[b];
+        good[j] = true;
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            H[3 * i + j] = W[3 * i] * is[0] * W[3 * j] + W[3 * i + 1] * is[1] * W[3 * j + 1]
-                           + W[3 * i + 2] * is[2] * W[3 * j + 2];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            R[3 * i + j] = A[3 * i] * H[j] + A[3 * i + 1] * H[3 + j] + A[3 * i + 2] * H[6 + j];
+            R[3 * i + j] = Bm[3 * i] * W[3 * j] + Bm[3 * i + 1] * W[3 * j + 1] + Bm[3 * i + 2] * W[3 * j + 2];
 }
 
 // From a 9-vector r_c (column-major vec of a near-rotation): SO(3)/O(3) projection,
