@@ -22,7 +22,7 @@ class Desc(ctypes.Structure):
         ("n_pts", ctypes.c_int32),
         ("n_lines", ctypes.c_int32),
         ("k_batched", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("anderson", ctypes.c_int32),
         ("K", ctypes.c_void_p),
         ("pts_2d", ctypes.c_void_p),
         ("pts_3d", ctypes.c_void_p),

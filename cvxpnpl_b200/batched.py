@@ -60,7 +60,7 @@ class Workspace:
 
 
 def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1e-9, max_iters=2500,
-                  sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, return_Z=False, return_obj=True, workspace=None,
+                  sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, return_Z=False, return_obj=True, workspace=None,
                   out: Optional[BatchedPoses] = None, device=None) -> BatchedPoses:
     """Solve B problems.  pts_2d [B,n,2], pts_3d [B,n,3], line_2d [B,m,2,2],
     line_3d [B,m,2,3], K [3,3] or [B,3,3]; any of the point / line pairs may be
@@ -129,6 +129,7 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.line_2d, d.line_3d = _ptr(line_2d if have_l else None), _ptr(line_3d if have_l else None)
         d.eps, d.max_iters, d.sweeps, d.rho_rel, d.alpha = float(eps), int(max_iters), int(sweeps), float(rho_rel), float(alpha)
         d.sigma = float(sigma)
+        d.anderson = 0 if anderson else -1
         d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
         d.workspace, d.workspace_bytes = _ptr(workspace.buf), workspace.nbytes
@@ -181,7 +182,7 @@ def assemble_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None):
     return Q, Bm
 
 
-def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0):
+def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True):
     """Q [B,9,9] -> (Z [B,10,10], dobj [B], iters [B], status [B]); the scs.solve
     call of cvxpnpl.py:478-492."""
     _require_cuda()
@@ -198,6 +199,7 @@ def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=
     d.batch = B
     d.eps, d.max_iters, d.sweeps, d.rho_rel, d.alpha = float(eps), int(max_iters), int(sweeps), float(rho_rel), float(alpha)
     d.sigma = float(sigma)
+    d.anderson = 0 if anderson else -1
     d.Z, d.obj, d.iters, d.status = _ptr(Z), _ptr(obj), _ptr(iters), _ptr(status)
     d.workspace, d.workspace_bytes = _ptr(ws.buf), ws.nbytes
     stream = torch.cuda.current_stream(device).cuda_stream

@@ -432,7 +432,8 @@ CVX_HD double jacobi_sweep(Arr<S> T, Arr<S> V)
 // Returns ||X - Z||_F^2, the fixed-point residual (primal residual X-Z and dual
 // residual rho (M+ - M)/alpha coincide up to scale).  Q/rho is read through `qr`
 // (45 packed entries of the 9x9 block); the eigenvalues through the strided view
-// L (10).  Also returns Z in z[] (registers).
+// L (10).  Also returns Z in z[] (registers) and writes the step g = alpha (X - Z)
+// (already added to M) to the strided view G for the Anderson accelerator.
 //
 // P_aff in closed form: the 15 triples are mutually orthogonal, so each is fixed by
 // subtracting its own normal component (the signed mean of its three entries when
@@ -446,7 +447,7 @@ CVX_HD double jacobi_sweep(Arr<S> T, Arr<S> V)
 // sigma ~ 1.5 cuts the iteration count by a third on PnP/PnPL.
 // ---------------------------------------------------------------------------------
 template <int S, class QR>
-CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, QR qr, double alpha, double isig, double z[55])
+CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, Arr<S> G, QR qr, double alpha, double isig, double z[55])
 {
 #pragma unroll
     for (int e = 0; e < 55; ++e) z[e] = 0.0;
@@ -484,6 +485,9 @@ CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, QR qr, double alpha, double 
         M[e0] = fma(alpha, d0, m0);                                                         \
         M[e1] = fma(alpha, d1, m1);                                                         \
         M[e2] = fma(alpha, d2, m2);                                                         \
+        G[e0] = alpha * d0;                                                                 \
+        G[e1] = alpha * d1;                                                                 \
+        G[e2] = alpha * d2;                                                                 \
         res += 2.0 * (d0 * d0 + d1 * d1 + d2 * d2);                                         \
     }
     CVX_TRIPLES(CVX_TRI)
@@ -498,28 +502,234 @@ CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, QR qr, double alpha, double 
         }
         md[9] = M[sidx(9, 9)];
         // D[r][c] = w[3c + r]; project onto unit row sums (over c) and column sums (over r)
-        double R[3], C[3], G = 0;
+        double R[3], C[3], Gs = 0;
 #pragma unroll
         for (int r = 0; r < 3; ++r) R[r] = w[r] + w[3 + r] + w[6 + r];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { C[c] = w[3 * c] + w[3 * c + 1] + w[3 * c + 2]; G += C[c]; }
+        for (int c = 0; c < 3; ++c) { C[c] = w[3 * c] + w[3 * c + 1] + w[3 * c + 2]; Gs += C[c]; }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const int i = 3 * c + r;
                 const double x = w[i] - (R[r] - 1.0) * (1.0 / 3.0) - (C[c] - 1.0) * (1.0 / 3.0)
-                                 + (G - 3.0) * (1.0 / 9.0);
+                                 + (Gs - 3.0) * (1.0 / 9.0);
                 const double d = x - z[sidx(i, i)];
                 M[sidx(i, i)] = fma(alpha, d, md[i]);
+                G[sidx(i, i)] = alpha * d;
                 res = fma(d, d, res);
             }
         const double d9 = 1.0 / (isig * isig) - z[sidx(9, 9)];
         M[sidx(9, 9)] = fma(alpha, d9, md[9]);
+        G[sidx(9, 9)] = alpha * d9;
         res = fma(d9, d9, res);
     }
 #undef CVX_Q
     return res;
+}
+
+// ---------------------------------------------------------------------------------
+// Anderson acceleration (type II, memory AA_M) of the DR fixed-point iteration
+// M <- F(M), the accelerator SCS itself relies on.  With g_k = F(M_k) - M_k:
+//     gamma = argmin || g_k - dG gamma ||,   M_{k+1} = M_k + g_k - (dM + dG) gamma
+// where the columns of dG / dM are the last AA_M differences of g and M.  History is
+// kept in FP32 in a strided L2-resident scratch (it only steers the extrapolation;
+// the fixed point, and hence the result, does not depend on it):
+//     H[0]            g_{k-1}
+//     H[1]            step_{k-1} = M_k - M_{k-1}
+//     H[2 + j]        dG_j                       j < AA_M
+//     H[2 + AA_M + j] dM_j + dG_j
+// each 55 packed entries.  Inner products weight off-diagonal entries twice
+// (Frobenius).  Safeguard: an extrapolated step longer than 10 |g_k| (or a singular
+// Gram matrix) is rejected, the history dropped and the plain step kept.
+// On entry M already holds M_k + g_k and G holds g_k; on exit M holds M_{k+1}.
+// ---------------------------------------------------------------------------------
+constexpr int AA_M = 3;
+constexpr double AA_RES2_ON = 0.05 * 0.05;   // accelerate only once ||X - Z||_F < 0.05 (|Z| ~ 4)
+constexpr int AA_ARRAYS = 2 + 2 * AA_M;       // g_prev, step_prev, dG[AA_M], (dM+dG)[AA_M]
+constexpr int AA_PITCH = 64;                  // words per array (55 used), 8 x 64 = 512 = all TMEM columns
+constexpr int AA_WORDS = AA_ARRAYS * AA_PITCH;
+
+struct AAState {
+    uint32_t mask;      // valid history columns (bit j = column j)
+    bool have_prev;     // g_prev / step_prev hold the previous iteration of THIS problem
+    float gram[AA_M][AA_M];   // dG'dG of the stored columns (lower triangle used), kept across steps
+};
+
+CVX_HD void aa_reset(AAState& aa)
+{
+    aa.mask = 0u;
+    aa.have_prev = false;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i)
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j) aa.gram[i][j] = 0.f;
+}
+
+// History accessors.  Both expose 8-word chunk loads/stores on array `arr`
+// (0 g_prev, 1 step_prev, 2+j dG_j, 2+AA_M+j dM_j+dG_j):
+//   * HistMem  -- plain strided memory (host harness; the stage kernel's global scratch)
+//   * HistTmem -- Blackwell tensor memory (pnpl_kernels.cu): every thread owns one TMEM
+//                 lane = 512 private 32-bit words, 12-cycle loads, no shared-memory or
+//                 L2 traffic.  tcgen05.ld/st are warp-collective with a warp-uniform
+//                 address, which is why aa_step below is written so that ALL lanes of a
+//                 warp execute every history access (column slots are warp-uniform,
+//                 lanes that do not accelerate just compute on dead data).
+struct HistMem {
+    float* p;
+    int64_t stride;
+    CVX_HD void ld8(int arr, int c, float o[8]) const
+    {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = p[(int64_t)(arr * AA_PITCH + c * 8 + u) * stride];
+    }
+    CVX_HD void st8(int arr, int c, const float v[8]) const
+    {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[(int64_t)(arr * AA_PITCH + c * 8 + u) * stride] = v[u];
+    }
+    CVX_HD void wait_ld() const {}
+    CVX_HD void wait_st() const {}
+    CVX_HD bool any(bool f) const { return f; }
+};
+
+// One accelerated step.  `active` lanes own a problem in the tail of its DR
+// iteration; `wslot` (warp-uniform, cycles 0..AA_M-1) is the column overwritten now.
+// On entry M holds M_k + g_k and G holds g_k (G[55] is a dedicated zero so whole
+// 8-word chunks can be processed without a bounds test); on exit (active lanes) M
+// holds M_{k+1}.  The least squares runs in FP32 and in the plain Euclidean metric of
+// the packed vector: it only steers the extrapolation, the fixed point does not
+// depend on it (measured: same iteration counts as the FP64 / Frobenius version).
+// The Gram matrix is kept across steps; only the row of the new column is recomputed.
+template <int S, class Hist>
+CVX_HD void aa_step(Arr<S> M, Arr<S> G, const Hist& H, AAState& aa, bool active, int wslot)
+{
+    static_assert(AA_M == 3, "the closed-form 3x3 solve below assumes AA_M == 3");
+    const bool close = active && aa.have_prev;
+    // ---- A. close the newest column (dG = g_k - g_{k-1}, dM + dG = step_{k-1} + dG);
+    //         dot products of the new column and of g with every stored column ----------
+    float rg0 = 0.f, rg1 = 0.f, rg2 = 0.f;   // col_j . g
+    float nd0 = 0.f, nd1 = 0.f, nd2 = 0.f;   // dg_new . col_j   (col_wslot is the one being replaced)
+    float ndd = 0.f, ndg = 0.f;              // dg_new . dg_new, dg_new . g
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+        float gp[8], sp[8], c0[8], c1[8], c2[8], dg[8], ss[8];
+        H.ld8(0, c, gp);
+        H.ld8(1, c, sp);
+        H.ld8(2, c, c0);
+        H.ld8(3, c, c1);
+        H.ld8(4, c, c2);
+        H.wait_ld();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float gf = (float)G[c * 8 + u];
+            const float d = gf - gp[u];
+            dg[u] = d;
+            ss[u] = sp[u] + d;
+            rg0 = fmaf(c0[u], gf, rg0);
+            rg1 = fmaf(c1[u], gf, rg1);
+            rg2 = fmaf(c2[u], gf, rg2);
+            nd0 = fmaf(c0[u], d, nd0);
+            nd1 = fmaf(c1[u], d, nd1);
+            nd2 = fmaf(c2[u], d, nd2);
+            ndd = fmaf(d, d, ndd);
+            ndg = fmaf(d, gf, ndg);
+        }
+        H.st8(2 + wslot, c, dg);
+        H.st8(2 + AA_M + wslot, c, ss);
+    }
+    // the overwritten slot is valid only if this lane had a previous iterate
+    aa.mask = close ? (aa.mask | (1u << wslot)) : (aa.mask & ~(1u << wslot));
+    if (!active) aa.mask = 0u;
+    // refresh row / column wslot of the Gram matrix and the right-hand side
+    float r[AA_M] = {rg0, rg1, rg2};
+    const float nd[AA_M] = {nd0, nd1, nd2};
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            // entry (i, j), i >= j, belongs to row/column wslot if i == wslot or j == wslot
+            if (i == wslot && j == wslot) aa.gram[i][j] = ndd;
+            else if (i == wslot) aa.gram[i][j] = nd[j];
+            else if (j == wslot) aa.gram[i][j] = nd[i];
+        }
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j)
+        if (j == wslot) r[j] = ndg;
+    // normal equations; columns that are not valid are cut out (they may hold NaN)
+    const bool v0 = aa.mask & 1u, v1 = aa.mask & 2u, v2 = aa.mask & 4u;
+    double a00 = v0 ? (double)aa.gram[0][0] : 0.0, a11 = v1 ? (double)aa.gram[1][1] : 0.0,
+           a22 = v2 ? (double)aa.gram[2][2] : 0.0;
+    const double a10 = (v1 && v0) ? (double)aa.gram[1][0] : 0.0, a20 = (v2 && v0) ? (double)aa.gram[2][0] : 0.0,
+                 a21 = (v2 && v1) ? (double)aa.gram[2][1] : 0.0;
+    const double r0 = v0 ? (double)r[0] : 0.0, r1 = v1 ? (double)r[1] : 0.0, r2 = v2 ? (double)r[2] : 0.0;
+    const double tr = a00 + a11 + a22;
+    a00 += 1e-7 * tr + (v0 ? 0.0 : 1.0);
+    a11 += 1e-7 * tr + (v1 ? 0.0 : 1.0);
+    a22 += 1e-7 * tr + (v2 ? 0.0 : 1.0);
+    // closed-form symmetric 3x3 solve (adjugate / determinant)
+    const double k00 = a11 * a22 - a21 * a21, k10 = a20 * a21 - a10 * a22, k20 = a10 * a21 - a20 * a11;
+    const double k11 = a00 * a22 - a20 * a20, k21 = a10 * a20 - a00 * a21, k22 = a00 * a11 - a10 * a10;
+    const double det = a00 * k00 + a10 * k10 + a20 * k20;
+    const double idet = 1.0 / det;
+    const double g0 = (k00 * r0 + k10 * r1 + k20 * r2) * idet;
+    const double g1 = (k10 * r0 + k11 * r1 + k21 * r2) * idet;
+    const double g2 = (k20 * r0 + k21 * r1 + k22 * r2) * idet;
+    const bool ok = active && aa.mask != 0u && tr > 0.0 && det > 0.0 && isfinite(g0) && isfinite(g1) && isfinite(g2);
+    const float f0 = (ok && v0) ? (float)g0 : 0.f, f1 = (ok && v1) ? (float)g1 : 0.f, f2 = (ok && v2) ? (float)g2 : 0.f;
+    H.wait_st();
+
+    // ---- B. extrapolate optimistically: M -= sum_j gamma_j (dM_j + dG_j); remember g_k
+    //         and the step; measure |step| against |g| ---------------------------------
+    float ng = 0.f, ns = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+        float c0[8], c1[8], c2[8], gk[8], stp[8];
+        H.ld8(2 + AA_M, c, c0);
+        H.ld8(3 + AA_M, c, c1);
+        H.ld8(4 + AA_M, c, c2);
+        H.wait_ld();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float gf = (float)G[c * 8 + u];
+            const float adj = fmaf(f0, c0[u], fmaf(f1, c1[u], f2 * c2[u]));
+            gk[u] = gf;
+            stp[u] = gf - adj;
+            if (ok) M[c * 8 + u] -= (double)adj;
+            ng = fmaf(gf, gf, ng);
+            ns = fmaf(stp[u], stp[u], ns);
+        }
+        H.st8(0, c, gk);
+        H.st8(1, c, stp);
+    }
+    H.wait_st();
+    // ---- C. (rare) the extrapolated step is longer than 10 |g|: undo, keep the plain
+    //         step, drop the history -----------------------------------------------------
+    const bool reject = ok && !(ns <= 100.f * ng);
+    if (H.any(reject)) {
+#pragma unroll 1
+        for (int c = 0; c < 7; ++c) {
+            float c0[8], c1[8], c2[8], gk[8], stp[8];
+            H.ld8(2 + AA_M, c, c0);
+            H.ld8(3 + AA_M, c, c1);
+            H.ld8(4 + AA_M, c, c2);
+            H.ld8(0, c, gk);
+            H.ld8(1, c, stp);
+            H.wait_ld();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float adj = fmaf(f0, c0[u], fmaf(f1, c1[u], f2 * c2[u]));
+                if (reject) {
+                    M[c * 8 + u] += (double)adj;
+                    stp[u] = gk[u];
+                }
+            }
+            H.st8(1, c, stp);
+        }
+        H.wait_st();
+    }
+    if (active && aa.mask != 0u && (!ok || reject)) aa.mask = 0u;
+    aa.have_prev = active;
 }
 
 // ---------------------------------------------------------------------------------

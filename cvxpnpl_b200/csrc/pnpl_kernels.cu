@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int NT = 128;                    // problems (threads) per CTA
-constexpr int SMEM_DOUBLES = 220;          // V 100 + M 55 + T 55 + lambda 10
+constexpr int SMEM_DOUBLES = 221;          // V 100 + M 55 + T 55 (+1 zero pad) + lambda 10
 constexpr size_t SMEM_BYTES = (size_t)NT * SMEM_DOUBLES * sizeof(double);
 
 thread_local char g_err[512] = "";
@@ -33,6 +33,63 @@ int fail(int code, const char* msg)
 }
 
 using cvx::Opts;
+
+// ---------------------------------------------------------------------------------
+// Tensor memory as a per-thread scratchpad.  The CTA owns all 512 TMEM columns; warp
+// w addresses lanes 32 (w % 4) .. +31, so each of the 128 threads has one TMEM lane
+// = 512 private 32-bit words: the Anderson history (8 arrays x 64 words).  The
+// tensor cores themselves are idle in this kernel (no dense contraction at 10x10);
+// their memory is not.  SASS: LDTM / STTM.
+// ---------------------------------------------------------------------------------
+struct HistTmem {
+    uint32_t base;   // TMEM address of column 0 in this warp's lane window
+    __device__ __forceinline__ void ld8(int arr, int c, float o[8]) const
+    {
+        uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                     : "r"(base + (uint32_t)(arr * cvx::AA_PITCH + c * 8))
+                     : "memory");
+        o[0] = __uint_as_float(r0); o[1] = __uint_as_float(r1); o[2] = __uint_as_float(r2); o[3] = __uint_as_float(r3);
+        o[4] = __uint_as_float(r4); o[5] = __uint_as_float(r5); o[6] = __uint_as_float(r6); o[7] = __uint_as_float(r7);
+    }
+    __device__ __forceinline__ void st8(int arr, int c, const float v[8]) const
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :
+                     : "r"(base + (uint32_t)(arr * cvx::AA_PITCH + c * 8)), "r"(__float_as_uint(v[0])),
+                       "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                       "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+                       "r"(__float_as_uint(v[7]))
+                     : "memory");
+    }
+    __device__ __forceinline__ void wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ bool any(bool f) const { return __any_sync(0xffffffffu, f) != 0; }
+};
+
+__device__ __forceinline__ uint32_t tmem_alloc_all(uint32_t* slot_smem)
+{
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(slot_smem)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *slot_smem;
+}
+
+__device__ __forceinline__ void tmem_free_all(uint32_t taddr)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(512) : "memory");
+}
 
 __device__ __forceinline__ const double* problem_K(const cvxpnpl_b200_desc& d, int64_t b)
 {
@@ -62,14 +119,25 @@ __global__ void __launch_bounds__(NT, 1)
 solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, int64_t ws_stride)
 {
     extern __shared__ double smem[];
+    __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x;
     const int64_t slot = (int64_t)blockIdx.x * NT + tid;
 
     cvx::Arr<NT> V{smem + tid};
     cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
     cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
-    cvx::Arr<NT> L{smem + (size_t)210 * NT + tid};
+    cvx::Arr<NT> L{smem + (size_t)211 * NT + tid};
     cvx::GArr QR{d.workspace + slot, ws_stride};
+    const uint32_t tmem_base = tmem_alloc_all(&tmem_slot);
+    const HistTmem H{tmem_base + ((uint32_t)((tid >> 5) & 3) << 21)};   // lane window 32*(warp%4), lane field = bits 31:16
+    T[55] = 0.0;   // zero pad read by the 8-word chunks of aa_step
+    {
+        // tensor memory comes up uninitialised: zero the history (the pad words must be 0)
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int arr = 0; arr < cvx::AA_ARRAYS; ++arr)
+            for (int c = 0; c < 8; ++c) H.st8(arr, c, zero);
+        H.wait_st();
+    }
 
     int64_t b = -1;
     bool exhausted = false;
@@ -81,6 +149,9 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, int
     st.phase = 0;
     st.rho = 0.0;
     st.dobj = 0.0;
+    st.res_prev = 1e300;
+    cvx::aa_reset(st.aa);
+    int wslot = 0;   // warp-uniform history column
     for (;;) {
         if (b < 0 && !exhausted) {
             const unsigned long long nb = atomicAdd(counter, 1ULL);
@@ -92,8 +163,14 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, int
             }
         }
         if (__all_sync(0xffffffffu, b < 0)) break;   // queue empty and every lane idle
+        bool want = false;
+        if (b >= 0) want = cvx::pass_dr(o, V, M, T, L, QR, st);
+        __syncwarp();
+        // warp-collective Anderson step: executed by all 32 lanes whenever one wants it
+        if (H.any(want)) cvx::aa_step(M, T, H, st.aa, want, wslot);
+        wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
         if (b >= 0) {
-            if (cvx::problem_pass(o, V, M, T, L, QR, st)) {
+            if (cvx::pass_eig(o, V, M, T, L, QR, st)) {
                 cvx::Result rs;
                 cvx::problem_finish(problem_at(d, b), o, V, M, T, L, QR, st, d.R + b * 36, d.t + b * 12,
                                     d.Z ? d.Z + b * 100 : nullptr, rs);
@@ -108,6 +185,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, int
             }
         }
     }
+    tmem_free_all(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------
@@ -127,53 +205,66 @@ __global__ void assemble_kernel(cvxpnpl_b200_desc d, double* Q, double* Bmat)
 }
 
 __global__ void __launch_bounds__(NT, 1)
-solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, int64_t ws_stride)
+solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, float* hist, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
-    const int64_t b = (int64_t)blockIdx.x * NT + tid;
-    if (b >= d.batch) return;
+    const int64_t slot = (int64_t)blockIdx.x * NT + tid;
     cvx::Arr<NT> V{smem + tid};
     cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
     cvx::Arr<NT> T{smem + (size_t)155 * NT + tid};
-    cvx::Arr<NT> L{smem + (size_t)210 * NT + tid};
-    cvx::GArr qr{d.workspace + b, ws_stride};
-    const double* Qi = Q + b * 81;
-    double nq = 0;
-    for (int i = 0; i < 9; ++i)
-        for (int j = 0; j < 9; ++j) nq = fma(Qi[9 * i + j], Qi[9 * i + j], nq);
-    cvx::LaneState st;
-    st.rho = o.rho_rel * sqrt(nq);
-    st.finite = (st.rho > 0.0) && isfinite(st.rho);
-    st.iterating = st.finite;
-    st.converged = false;
-    st.it = 0;
-    st.phase = 0;
-    st.dobj = 0.0;
-    for (int i = 0; i < 9; ++i)
-        for (int j = 0; j <= i; ++j) qr[cvx::sidx(i, j)] = 0.5 * (Qi[9 * i + j] + Qi[9 * j + i]) / st.rho;
-    for (int i = 0; i < 10; ++i) {
-        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
-        for (int j = 0; j <= i; ++j) M[cvx::sidx(i, j)] = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
-        L[i] = (i == 9) ? o.sigma * o.sigma : 1.0 / 3.0;
-    }
-    for (int guard = 0; guard < o.max_iters + 40; ++guard)
-        if (cvx::problem_pass(o, V, M, T, L, qr, st)) break;
-    double lam[10];
-    for (int j = 0; j < 10; ++j) lam[j] = L[j];
-    int32_t status = cvx::ST_NAN;
-    if (st.finite) {
-        status = st.converged ? cvx::ST_OK : cvx::ST_MAX_ITERS;
-        for (int j = 0; j < 10; ++j)
-            if (!isfinite(lam[j])) status = cvx::ST_NAN;
-    }
-    const double dobj = (status != cvx::ST_NAN) ? st.dobj : nan("");
-    if (d.Z) cvx::write_Z(V, lam, status == cvx::ST_NAN, d.Z + b * 100);
-    if (d.status) d.status[b] = status;
-    if (d.iters) d.iters[b] = st.it;
-    if (d.obj) {
-        d.obj[2 * b] = nan("");
-        d.obj[2 * b + 1] = dobj;
+    cvx::Arr<NT> L{smem + (size_t)211 * NT + tid};
+    cvx::GArr qr{d.workspace + slot, ws_stride};
+    const cvx::HistMem H{hist + slot, ws_stride};
+    T[55] = 0.0;
+    for (int arr = 0; arr < cvx::AA_ARRAYS; ++arr)
+        for (int e = 0; e < cvx::AA_PITCH; ++e) hist[slot + (int64_t)(arr * cvx::AA_PITCH + e) * ws_stride] = 0.f;
+    for (int64_t b = slot; b < d.batch; b += (int64_t)gridDim.x * NT) {
+        const double* Qi = Q + b * 81;
+        double nq = 0;
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j < 9; ++j) nq = fma(Qi[9 * i + j], Qi[9 * i + j], nq);
+        cvx::LaneState st;
+        st.rho = o.rho_rel * sqrt(nq);
+        st.finite = (st.rho > 0.0) && isfinite(st.rho);
+        st.iterating = st.finite;
+        st.converged = false;
+        st.it = 0;
+        st.phase = 0;
+        st.dobj = 0.0;
+        cvx::aa_reset(st.aa);
+        st.res_prev = 1e300;
+        const double ir = 1.0 / st.rho;
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j <= i; ++j) qr[cvx::sidx(i, j)] = (0.5 * (Qi[9 * i + j] + Qi[9 * j + i])) * ir;
+        for (int i = 0; i < 10; ++i) {
+            for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
+            for (int j = 0; j <= i; ++j) M[cvx::sidx(i, j)] = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
+            L[i] = (i == 9) ? o.sigma * o.sigma : 1.0 / 3.0;
+        }
+        int wslot = 0;
+        for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+            const bool want = cvx::pass_dr(o, V, M, T, L, qr, st);
+            if (want) cvx::aa_step(M, T, H, st.aa, want, wslot);
+            wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
+            if (cvx::pass_eig(o, V, M, T, L, qr, st)) break;
+        }
+        double lam[10];
+        for (int j = 0; j < 10; ++j) lam[j] = L[j];
+        int32_t status = cvx::ST_NAN;
+        if (st.finite) {
+            status = st.converged ? cvx::ST_OK : cvx::ST_MAX_ITERS;
+            for (int j = 0; j < 10; ++j)
+                if (!isfinite(lam[j])) status = cvx::ST_NAN;
+        }
+        const double dobj = (status != cvx::ST_NAN) ? st.dobj : nan("");
+        if (d.Z) cvx::write_Z(V, lam, status == cvx::ST_NAN, d.Z + b * 100);
+        if (d.status) d.status[b] = status;
+        if (d.iters) d.iters[b] = st.it;
+        if (d.obj) {
+            d.obj[2 * b] = nan("");
+            d.obj[2 * b + 1] = dobj;
+        }
     }
 }
 
@@ -262,14 +353,33 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     o.alpha = d->alpha > 0 ? d->alpha : 1.3;
     o.rho_rel = d->rho_rel > 0 ? d->rho_rel : 0.01;
     o.sigma = d->sigma > 0 ? d->sigma : 1.5;
+    o.anderson = d->anderson >= 0;
     o.max_iters = d->max_iters > 0 ? d->max_iters : 2500;
     o.sweeps = d->sweeps > 0 ? d->sweeps : 1;
     return o;
 }
 
-int64_t ws_stride_for(int64_t batch) { return ((batch + NT - 1) / NT) * NT; }
-constexpr int64_t PERSISTENT_SLOTS = 1024 * NT;   // >= (#SMs of any device) * NT
 constexpr int64_t WS_HEADER_DOUBLES = 16;
+
+// thread slots of the persistent grid: one CTA of NT threads per SM.  Without a
+// CUDA device (CPU-side callers sizing buffers) a generous 256 SMs is assumed.
+int64_t device_slots()
+{
+    int dev = 0, n_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) {
+        cudaGetLastError();
+        n_sm = 256;
+    }
+    return (int64_t)n_sm * NT;
+}
+
+// workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | AA history AA_WORDS x slots floats
+// (the history region is used by the stage kernel only; the fused kernel keeps it in TMEM)]
+size_t ws_bytes_for_slots(int64_t slots)
+{
+    return (WS_HEADER_DOUBLES + (size_t)slots * 45) * sizeof(double) + (size_t)slots * cvx::AA_WORDS * sizeof(float);
+}
 
 }  // namespace
 
@@ -282,10 +392,8 @@ int cvxpnpl_b200_last_launch_count(void) { return g_launches; }
 size_t cvxpnpl_b200_workspace_bytes(int64_t batch)
 {
     if (batch <= 0) return 0;
-    // work counter (header) + Q/rho scratch [45][slots]; slots = padded batch for the
-    // stage kernel, at most PERSISTENT_SLOTS thread slots for the persistent one
-    const int64_t slots = ws_stride_for(batch) > PERSISTENT_SLOTS ? ws_stride_for(batch) : PERSISTENT_SLOTS;
-    return ((size_t)slots * 45 + WS_HEADER_DOUBLES) * sizeof(double);
+    // independent of the batch size: the scratch is per thread slot of the persistent grid
+    return ws_bytes_for_slots(device_slots());
 }
 
 int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
@@ -307,22 +415,18 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
         attr_set = true;
     }
-    int dev = 0, n_sm = 0;
-    cudaError_t e0 = cudaGetDevice(&dev);
-    if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
+    const int64_t slots = device_slots();
     // persistent grid: one CTA per SM (shared memory allows exactly one), never more
     // CTAs than there is work for
     const int64_t want = (d->batch + NT - 1) / NT;
-    const int64_t blocks = want < n_sm ? want : n_sm;
-    // the work counter lives in front of the Q/rho scratch
+    const int64_t blocks = want < slots / NT ? want : slots / NT;
+    // the work counter lives in front of the Q/rho scratch, the AA history behind it
     unsigned long long* counter = (unsigned long long*)d->workspace;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
-    e0 = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+    cudaError_t e0 = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), (cudaStream_t)stream);
     if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
-    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter,
-                                                                                  PERSISTENT_SLOTS);
+    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter, slots);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
@@ -377,11 +481,13 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int64_t blocks = (d->batch + NT - 1) / NT;
+    const int64_t slots = device_slots();
+    const int64_t want = (d->batch + NT - 1) / NT;
+    const int64_t blocks = want < slots / NT ? want : slots / NT;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
-    solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), Q,
-                                                                                ws_stride_for(d->batch));
+    float* hist = (float*)(dd.workspace + slots * 45);
+    solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), Q, hist, slots);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));

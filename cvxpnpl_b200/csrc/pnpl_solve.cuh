@@ -15,6 +15,7 @@ struct Opts {
     int max_iters;
     int sweeps;       // Jacobi sweeps per iteration (warm started)
     double sigma;     // homogeneous-coordinate scaling (see dr_step)
+    bool anderson;    // Anderson acceleration of the DR iteration (see aa_step)
 };
 
 struct Problem {
@@ -41,8 +42,10 @@ struct Result {
 // no lane waits for the slowest problem of its warp / CTA (iteration counts vary
 // from ~250 to 2500).  The three phases:
 //     problem_begin   assembly, rho, Q/rho, start point
-//     problem_pass    one DR iteration + warm-started Jacobi sweep (or, once the DR
-//                     loop has stopped, one more pass that polishes the
+//     pass_dr         one DR iteration (returns whether the lane wants an Anderson step)
+//     aa_step         warp-uniform Anderson extrapolation (history in tensor memory)
+//     pass_eig        basis change + warm-started Jacobi sweep (or, once the DR loop
+//                     has stopped, one more pass that polishes the
 //                     eigen-decomposition); returns true when the problem is done
 //     problem_finish  dual objective, optional Z, pose extraction
 // V (100), M (55), T (55), L (10) are the problem's strided work arrays (220
@@ -51,12 +54,14 @@ struct Result {
 // ---------------------------------------------------------------------------------
 struct LaneState {
     double rho, dobj;
+    double res_prev;   // squared residual of the previous DR iteration
     int32_t it;
     // phase 0: DR iterations; 1: polishing the eigen-decomposition of the last
     // (scaled) iterate; 2: eigen-decomposition of the unscaled Z (only when sigma != 1
     // and the solution may have rank > 1)
     int32_t phase;
     bool finite, iterating, converged;
+    AAState aa;
 };
 
 template <int S, class QRT>
@@ -92,6 +97,8 @@ CVX_HD void problem_begin(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
     st.dobj = 0.0;
     st.phase = 0;
     st.it = 0;
+    aa_reset(st.aa);
+    st.res_prev = 1e300;
     st.finite = finite;
     st.iterating = finite;
     st.converged = false;
@@ -103,23 +110,46 @@ CVX_HD void problem_begin(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
 template <int S, class QR>
 CVX_HD double dual_objective(Arr<S> V, Arr<S> L, QR qr, double rho, double sigma);
 
+// Part 1 of a pass: one DR iteration (if the problem is still iterating).  Returns
+// true when the lane wants an Anderson step on the iterate it just produced.
 template <int S, class QRT>
-CVX_HD bool problem_pass(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR, LaneState& st)
+CVX_HD bool pass_dr(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR, LaneState& st)
+{
+    if (!st.finite || !st.iterating) return false;
+    double z[55];
+    const double res = dr_step(M, V, L, T, QR, o.alpha, 1.0 / o.sigma, z);
+    ++st.it;
+#if defined(CVX_TRACE) && !defined(__CUDA_ARCH__)
+    printf("it %d res %.3e aa_mask %u\n", st.it, sqrt(res), st.aa.mask);
+#endif
+    if (!(res > o.eps2)) {  // also leaves on NaN
+        st.converged = (res <= o.eps2);
+        st.iterating = false;
+        st.phase = 1;
+        return false;
+    }
+    if (st.it >= o.max_iters) {
+        st.iterating = false;
+        st.phase = 1;
+        return false;
+    }
+    if (!o.anderson) return false;
+    // Anderson acceleration only in the (locally linear) tail of the iteration:
+    // extrapolating during the early active-set changes can throw M far away, from
+    // where DR needs thousands of constant-length steps to walk back.  A residual
+    // that grows by more than 2x after an accelerated step drops the history.
+    const bool tail = res < AA_RES2_ON;
+    if (!tail || res > 4.0 * st.res_prev) aa_reset(st.aa);
+    st.res_prev = res;
+    return tail;   // T holds the step g until the basis change in pass_eig
+}
+
+// Part 2 of a pass: basis change + warm-started Jacobi sweep; phase transitions.
+// Returns true when the problem is done.
+template <int S, class QRT>
+CVX_HD bool pass_eig(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR, LaneState& st)
 {
     if (!st.finite) return true;
-    if (st.iterating) {
-        double z[55];
-        const double res = dr_step(M, V, L, QR, o.alpha, 1.0 / o.sigma, z);
-        ++st.it;
-        if (!(res > o.eps2)) {  // also leaves on NaN
-            st.converged = (res <= o.eps2);
-            st.iterating = false;
-            st.phase = 1;
-        } else if (st.it >= o.max_iters) {
-            st.iterating = false;
-            st.phase = 1;
-        }
-    }
     rotate_into_basis(M, V, T);
     double t[55];
 #pragma unroll
@@ -233,16 +263,21 @@ CVX_HD void problem_finish(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M,
     rs.dobj = dobj;
 }
 
-// The whole path for one problem, sequentially (host harness, stage kernels).
-template <int S, class QRT>
+// The whole path for one problem, sequentially (host harness).
+template <int S, class QRT, class Hist>
 CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR,
-                          double* R_out, double* t_out, double* Z_out, Result& rs)
+                          const Hist& H, double* R_out, double* t_out, double* Z_out, Result& rs)
 {
     LaneState st;
     problem_begin(pr, o, V, M, L, QR, st);
+    int wslot = 0;
 #pragma unroll 1
-    for (int guard = 0; guard < o.max_iters + 40; ++guard)
-        if (problem_pass(o, V, M, T, L, QR, st)) break;
+    for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+        const bool want = pass_dr(o, V, M, T, L, QR, st);
+        if (H.any(want)) aa_step(M, T, H, st.aa, want, wslot);
+        wslot = (wslot + 1 == AA_M) ? 0 : wslot + 1;
+        if (pass_eig(o, V, M, T, L, QR, st)) break;
+    }
     problem_finish(pr, o, V, M, T, L, QR, st, R_out, t_out, Z_out, rs);
 }
 

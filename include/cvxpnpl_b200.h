@@ -52,7 +52,7 @@ typedef struct cvxpnpl_b200_desc {
     int32_t n_pts;          /* points per problem (may be 0) */
     int32_t n_lines;        /* lines per problem (may be 0) */
     int32_t k_batched;      /* 0: K is [3,3]; else [B,3,3] */
-    int32_t reserved0;
+    int32_t anderson;       /* Anderson acceleration of the ADMM iteration: 0 = default (on), -1 = off */
     const double* K;
     const double* pts_2d;
     const double* pts_3d;

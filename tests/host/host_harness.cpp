@@ -13,7 +13,7 @@
 extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
                           const double* pts_2d, const double* pts_3d, const double* line_2d,
                           const double* line_3d, double eps, int max_iters, int sweeps, double rho_rel,
-                          double alpha, double sigma, double* R, double* t, int32_t* n_poses, int32_t* status,
+                          double alpha, double sigma, int anderson, double* R, double* t, int32_t* n_poses, int32_t* status,
                           int32_t* iters, double* obj, double* Z)
 {
     cvx::Opts o;
@@ -23,7 +23,9 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
     o.max_iters = max_iters > 0 ? max_iters : 2500;
     o.sweeps = sweeps > 0 ? sweeps : 1;
     o.sigma = sigma > 0 ? sigma : 1.5;
-    std::vector<double> V(100), M(55), T(55), L(10), qr(45);
+    o.anderson = anderson != 0;
+    std::vector<double> V(100), M(56), T(56), L(10), qr(45);   // T[55] = 0: zero pad for aa_step
+    std::vector<float> hist(cvx::AA_WORDS);
     for (int64_t b = 0; b < B; ++b) {
         cvx::Problem pr;
         pr.K = k_batched ? K + 9 * b : K;
@@ -35,7 +37,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
         pr.n_lines = n_lines;
         cvx::Result rs;
         cvx::solve_problem(pr, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{M.data()}, cvx::Arr<1>{T.data()},
-                           cvx::Arr<1>{L.data()}, cvx::Arr<1>{qr.data()},
+                           cvx::Arr<1>{L.data()}, cvx::Arr<1>{qr.data()}, cvx::HistMem{hist.data(), 1},
                            R + b * 36, t + b * 12, Z ? Z + b * 100 : nullptr, rs);
         n_poses[b] = rs.n_poses;
         status[b] = rs.status;
