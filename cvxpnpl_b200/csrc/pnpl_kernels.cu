@@ -116,7 +116,7 @@ __device__ __forceinline__ cvx::Problem problem_at(const cvxpnpl_b200_desc& d, i
 // of the batch (median ~300, tail to 2500) costs no idle lanes.
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1)
-solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, int64_t ws_stride)
+solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, double* park, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
@@ -171,21 +171,40 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, int
         wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
         if (b >= 0) {
             if (cvx::pass_eig(o, V, M, T, L, QR, st)) {
-                cvx::Result rs;
-                cvx::problem_finish(problem_at(d, b), o, V, M, T, L, QR, st, d.R + b * 36, d.t + b * 12,
-                                    d.Z ? d.Z + b * 100 : nullptr, rs);
-                d.n_poses[b] = rs.n_poses;
-                d.status[b] = rs.status;
-                d.iters[b] = rs.iters;
-                if (d.obj) {
-                    d.obj[2 * b] = rs.pobj;
-                    d.obj[2 * b + 1] = rs.dobj;
-                }
+                // park the eigen-decomposition; poses are extracted by finish_kernel
+                cvx::problem_park(V, L, st, park + b * cvx::PARK_DOUBLES, d.iters + b);
                 b = -1;
             }
         }
     }
     tmem_free_all(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------
+// Finish kernel: parked eigen-decompositions -> poses, one thread per problem, fully
+// lane-parallel (re-assembly, rank test, rank-1 / multi-solution recovery, SVD
+// projection, translation, optimality flag, optional Z).
+// ---------------------------------------------------------------------------------
+constexpr int NT_F = 64;
+constexpr size_t SMEM_F_BYTES = (size_t)NT_F * 172 * sizeof(double);   // V 100 + Q 45 + B 27
+__global__ void __launch_bounds__(NT_F) finish_kernel(cvxpnpl_b200_desc d, Opts o, const double* park)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * NT_F + tid;
+    if (b >= d.batch) return;
+    cvx::Arr<NT_F> V{smem + tid};
+    cvx::Arr<NT_F> Qs{smem + (size_t)100 * NT_F + tid};
+    cvx::Arr<NT_F> Bs{smem + (size_t)145 * NT_F + tid};
+    cvx::Result rs;
+    cvx::extract_parked(problem_at(d, b), o, park + b * cvx::PARK_DOUBLES, V, Qs, Bs, d.R + b * 36, d.t + b * 12,
+                        d.Z ? d.Z + b * 100 : nullptr, rs);
+    d.n_poses[b] = rs.n_poses;
+    d.status[b] = rs.status;
+    if (d.obj) {
+        d.obj[2 * b] = rs.pobj;
+        d.obj[2 * b + 1] = rs.dobj;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -374,11 +393,12 @@ int64_t device_slots()
     return (int64_t)n_sm * NT;
 }
 
-// workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | AA history AA_WORDS x slots floats
-// (the history region is used by the stage kernel only; the fused kernel keeps it in TMEM)]
-size_t ws_bytes_for_slots(int64_t slots)
+// workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | parked results 112 x batch doubles |
+//                    AA history AA_WORDS x slots floats (stage kernel only; the fused kernel uses TMEM)]
+size_t ws_bytes_for(int64_t slots, int64_t batch)
 {
-    return (WS_HEADER_DOUBLES + (size_t)slots * 45) * sizeof(double) + (size_t)slots * cvx::AA_WORDS * sizeof(float);
+    return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * cvx::PARK_DOUBLES) * sizeof(double) +
+           (size_t)slots * cvx::AA_WORDS * sizeof(float);
 }
 
 }  // namespace
@@ -392,8 +412,7 @@ int cvxpnpl_b200_last_launch_count(void) { return g_launches; }
 size_t cvxpnpl_b200_workspace_bytes(int64_t batch)
 {
     if (batch <= 0) return 0;
-    // independent of the batch size: the scratch is per thread slot of the persistent grid
-    return ws_bytes_for_slots(device_slots());
+    return ws_bytes_for(device_slots(), batch);
 }
 
 int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
@@ -412,6 +431,8 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(solve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_F_BYTES);
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
         attr_set = true;
     }
@@ -424,10 +445,14 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     unsigned long long* counter = (unsigned long long*)d->workspace;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
+    double* park = dd.workspace + slots * 45;
     cudaError_t e0 = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), (cudaStream_t)stream);
     if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
-    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter, slots);
-    g_launches = 1;
+    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter, park,
+                                                                                  slots);
+    finish_kernel<<<(unsigned)((d->batch + NT_F - 1) / NT_F), NT_F, SMEM_F_BYTES, (cudaStream_t)stream>>>(
+        dd, make_opts(d), park);
+    g_launches = 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     return 0;
@@ -486,7 +511,7 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
     const int64_t blocks = want < slots / NT ? want : slots / NT;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
-    float* hist = (float*)(dd.workspace + slots * 45);
+    float* hist = (float*)(dd.workspace + slots * 45 + d->batch * cvx::PARK_DOUBLES);
     solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), Q, hist, slots);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();

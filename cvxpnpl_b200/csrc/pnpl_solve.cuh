@@ -263,6 +263,57 @@ CVX_HD void problem_finish(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M,
     rs.dobj = dobj;
 }
 
+// Deferred finish.  Inside the persistent kernel a finishing lane runs alone (the
+// other 31 lanes of its warp wait), so everything expensive at the end of a problem
+// -- re-assembly, the 3x3 SVD projections, the multi-solution recovery -- is NOT
+// done there: the lane only parks its eigen-decomposition (V 100, lambda 10, dual
+// objective, preliminary status = 112 doubles) in global memory, and a second, fully
+// lane-parallel kernel (extract_parked) turns it into poses.  ncu: the in-loop
+// finish cost 13 % of the warp-issue samples before the split.
+constexpr int PARK_DOUBLES = 112;
+
+template <int S>
+CVX_HD void problem_park(Arr<S> V, Arr<S> L, const LaneState& st, double* park, int32_t* iters_out)
+{
+    int32_t status = ST_NAN;
+    if (st.finite) {
+        status = st.converged ? ST_OK : ST_MAX_ITERS;
+#pragma unroll 1
+        for (int j = 0; j < 10; ++j)
+            if (!isfinite(L[j])) status = ST_NAN;
+    }
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) park[e] = V[e];
+#pragma unroll 2
+    for (int j = 0; j < 10; ++j) park[100 + j] = L[j];
+    park[110] = (status != ST_NAN) ? st.dobj : nan("");
+    park[111] = (double)status;
+    *iters_out = st.it;
+}
+
+// second half of the finish: from the parked state to poses.  V is a strided work
+// array (100) that receives the parked eigenvectors, Qs (45) / Bs (27) receive the
+// re-assembled problem.
+template <int S>
+CVX_HD void extract_parked(const Problem& pr, const Opts& o, const double* park, Arr<S> V, Arr<S> Qs, Arr<S> Bs,
+                           double* R_out, double* t_out, double* Z_out, Result& rs)
+{
+    double lam[10];
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) V[e] = park[e];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) lam[j] = park[100 + j];
+    const double dobj = park[110];
+    int32_t status = (int32_t)park[111];
+    if (Z_out) write_Z(V, lam, status == ST_NAN, Z_out);
+    if (status != ST_NAN) assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
+    double pobj;
+    rs.n_poses = extract_poses(V, lam, Qs, Bs, status, dobj, sqrt(o.eps2), R_out, t_out, pobj);
+    rs.status = status;
+    rs.pobj = pobj;
+    rs.dobj = dobj;
+}
+
 // The whole path for one problem, sequentially (host harness).
 template <int S, class QRT, class Hist>
 CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT QR,
