@@ -116,7 +116,8 @@ __device__ __forceinline__ cvx::Problem problem_at(const cvxpnpl_b200_desc& d, i
 // of the batch (median ~300, tail to 2500) costs no idle lanes.
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1)
-solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, double* park, int64_t ws_stride)
+solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, const double* pre, double* park,
+                   int64_t ws_stride)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
@@ -157,7 +158,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, dou
             const unsigned long long nb = atomicAdd(counter, 1ULL);
             if (nb < (unsigned long long)d.batch) {
                 b = (int64_t)nb;
-                cvx::problem_begin(problem_at(d, b), o, V, M, L, QR, st);
+                cvx::problem_begin(pre + b * cvx::PRE_DOUBLES, o, V, M, L, QR, st);
             } else {
                 exhausted = true;
             }
@@ -178,6 +179,17 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, dou
         }
     }
     tmem_free_all(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------
+// Pre-pass kernel: correspondences -> Q/rho and rho per problem (46 doubles), one
+// thread per problem, lane-parallel.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.batch) return;
+    cvx::assemble_scaled(problem_at(d, b), o, pre + b * cvx::PRE_DOUBLES);
 }
 
 // ---------------------------------------------------------------------------------
@@ -394,10 +406,12 @@ int64_t device_slots()
 }
 
 // workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | parked results 112 x batch doubles |
+//                    pre-pass 46 x batch doubles |
 //                    AA history AA_WORDS x slots floats (stage kernel only; the fused kernel uses TMEM)]
 size_t ws_bytes_for(int64_t slots, int64_t batch)
 {
-    return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * cvx::PARK_DOUBLES) * sizeof(double) +
+    return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES)) *
+               sizeof(double) +
            (size_t)slots * cvx::AA_WORDS * sizeof(float);
 }
 
@@ -446,13 +460,15 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
     double* park = dd.workspace + slots * 45;
+    double* pre = park + d->batch * cvx::PARK_DOUBLES;
     cudaError_t e0 = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), (cudaStream_t)stream);
     if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
-    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter, park,
-                                                                                  slots);
+    pre_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dd, make_opts(d), pre);
+    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter, pre,
+                                                                                  park, slots);
     finish_kernel<<<(unsigned)((d->batch + NT_F - 1) / NT_F), NT_F, SMEM_F_BYTES, (cudaStream_t)stream>>>(
         dd, make_opts(d), park);
-    g_launches = 2;
+    g_launches = 3;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     return 0;
@@ -511,7 +527,7 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
     const int64_t blocks = want < slots / NT ? want : slots / NT;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
-    float* hist = (float*)(dd.workspace + slots * 45 + d->batch * cvx::PARK_DOUBLES);
+    float* hist = (float*)(dd.workspace + slots * 45 + d->batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES));
     solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), Q, hist, slots);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();

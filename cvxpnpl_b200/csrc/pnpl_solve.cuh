@@ -64,26 +64,39 @@ struct LaneState {
     AAState aa;
 };
 
-template <int S, class QRT>
-CVX_HD void problem_begin(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
+// Assembly for one problem into 46 doubles: Q/rho (45, packed) and rho.  Run by a
+// lane-parallel pre-pass kernel (pre_kernel) so that the persistent solver's
+// problem_begin -- which executes with a single active lane -- only has to copy.
+constexpr int PRE_DOUBLES = 46;
+
+template <class QOut>
+CVX_HD void assemble_scaled(const Problem& pr, const Opts& o, QOut out)
 {
-    // Q (45) and B (27) land in the V region, which is free until it is initialised
-    Arr<S> Qs = V;
-    Arr<S> Bs = V.sub(45);
-    bool finite = assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
+    double Q[45], Bm[27];
+    bool finite = assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Q, Bm);
     double nq = 0;
 #pragma unroll
     for (int i = 0; i < 9; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            const double q = Qs[sidx(i, j)];
+            const double q = Q[sidx(i, j)];
             nq = fma((i == j) ? 1.0 : 2.0, q * q, nq);
         }
     const double rho = o.rho_rel * sqrt(nq);
     finite = finite && (rho > 0.0) && isfinite(rho);
     const double ir = 1.0 / rho;
 #pragma unroll
-    for (int e = 0; e < 45; ++e) QR[e] = Qs[e] * ir;
+    for (int e = 0; e < 45; ++e) out[e] = Q[e] * ir;
+    out[45] = finite ? rho : nan("");
+}
+
+template <int S, class QRT>
+CVX_HD void problem_begin(const double* pre, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
+{
+#pragma unroll 5
+    for (int e = 0; e < 45; ++e) QR[e] = pre[e];
+    const double rho = pre[45];
+    const bool finite = isfinite(rho);
     // start: Z0 = blkdiag(I/3, 1) (feasible for the diagonal block), U0 = 0
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -320,7 +333,9 @@ CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
                           const Hist& H, double* R_out, double* t_out, double* Z_out, Result& rs)
 {
     LaneState st;
-    problem_begin(pr, o, V, M, L, QR, st);
+    double pre[PRE_DOUBLES];
+    assemble_scaled(pr, o, pre);
+    problem_begin(pre, o, V, M, L, QR, st);
     int wslot = 0;
 #pragma unroll 1
     for (int guard = 0; guard < o.max_iters + 40; ++guard) {
