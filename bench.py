@@ -321,7 +321,8 @@ def run_ours(a):
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": (kc["dram_bytes_read"] + kc["dram_bytes_write"]) if kc else None,
                          "peak_kind": peak_kind,
-                         "kernel": "solve_fused_kernel", "kernel_ms": ms_kernel,
+                         "kernel": "solve_fused_kernel (+ pre_kernel, finish_kernel: 1.7 % of the step)",
+                         "kernel_ms": ms_kernel,
                          "algorithmic_bytes_per_problem": bpp,
                          "note": "the path is compute/latency bound in shared memory + fp64 pipe, not HBM bound "
                                  "(SURVEY.md 8d): the HBM fraction is reported as asked, see DESIGN.md"},
