@@ -106,9 +106,11 @@ def run_reference(a):
         return
     cores = host_cores()
     pool = make_pool(cores)
-    # bounded sample per step: about 2 s of wall clock on all cores
-    r0, _ = cpu_rate(max(2 * cores, 16), a.n_pts, a.n_lines, a.noise, cores, pool)
-    sample = a.cpu_sample or max(cores, int(r0 * 2.0))
+    # bounded sample per step: about 3 s of wall clock on all cores (rate probed twice:
+    # the first probe also pays for the pool's start-up)
+    cpu_rate(max(2 * cores, 16), a.n_pts, a.n_lines, a.noise, cores, pool)
+    r0, _ = cpu_rate(max(8 * cores, 64), a.n_pts, a.n_lines, a.noise, cores, pool)
+    sample = a.cpu_sample or max(8 * cores, int(r0 * 3.0))
     for _ in range(a.warmup):
         cpu_rate(max(cores, sample // 4), a.n_pts, a.n_lines, a.noise, cores, pool)
     t0 = time.perf_counter()
@@ -342,8 +344,9 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             cores = host_cores()
             pool = make_pool(cores)
-            r0, _ = cpu_rate(max(2 * cores, 16), n_pts, n_lines, a.noise, cores, pool)
-            sample = a.cpu_sample or max(cores, int(r0 * 25.0))  # about 15-25 s of CPU work
+            cpu_rate(max(2 * cores, 16), n_pts, n_lines, a.noise, cores, pool)
+            r0, _ = cpu_rate(max(8 * cores, 64), n_pts, n_lines, a.noise, cores, pool)
+            sample = a.cpu_sample or max(8 * cores, int(r0 * 15.0))  # about 15 s of CPU work
             v, wall = cpu_rate(sample, n_pts, n_lines, a.noise, cores, pool)
             pool.close()
             line["cpu_baseline"] = {
