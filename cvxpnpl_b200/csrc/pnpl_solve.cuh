@@ -16,6 +16,7 @@ struct Opts {
     int sweeps;       // Jacobi sweeps per iteration (warm started)
     double sigma;     // homogeneous-coordinate scaling (see dr_step)
     bool anderson;    // Anderson acceleration of the DR iteration (see aa_step)
+    double aa_on2;    // squared residual below which Anderson acceleration is active
 };
 
 struct Problem {
@@ -151,7 +152,7 @@ CVX_HD bool pass_dr(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT Q
     // extrapolating during the early active-set changes can throw M far away, from
     // where DR needs thousands of constant-length steps to walk back.  A residual
     // that grows by more than 2x after an accelerated step drops the history.
-    const bool tail = res < AA_RES2_ON;
+    const bool tail = res < o.aa_on2;
     if (!tail || res > 4.0 * st.res_prev) aa_reset(st.aa);
     st.res_prev = res;
     return tail;   // T holds the step g until the basis change in pass_eig
