@@ -6,6 +6,6 @@ pnl_batched, pnpl_batched, solve_batched.
 """
 __version__ = "0.1.0"
 
-from .api import CvxPnPL, pnl, pnp, pnpl  # noqa: F401
+from .api import CvxPnPL, pnl, pnp, pnpl, rc  # noqa: F401
 from .batched import (BatchedPoses, Workspace, assemble_batched, extract_batched, pnl_batched,  # noqa: F401
                       pnp_batched, pnpl_batched, solve_batched, solve_sdp_batched, measure_fp64_peak)

@@ -31,6 +31,8 @@ class Desc(ctypes.Structure):
         ("eps", ctypes.c_double),
         ("max_iters", ctypes.c_int32),
         ("sweeps", ctypes.c_int32),
+        ("variant", ctypes.c_int32),
+        ("reserved1", ctypes.c_int32),
         ("rho_rel", ctypes.c_double),
         ("alpha", ctypes.c_double),
         ("sigma", ctypes.c_double),

@@ -102,3 +102,13 @@ class CvxPnPL:
         if n_p == 0:
             return pnl(line_2d, line_3d, K)
         return pnpl(pts_2d, line_2d, pts_3d, line_3d, K)
+
+
+def rc(pts_2d, pts_3d, K, eps: float = 1e-9, max_iters: int = 2500, verbose: bool = False) -> List[Pose]:
+    """The "rc" ablation of benchmarks/toolkit/methods/pnp.py:58-82 / rc.py: pnp with the
+    redundant row-orthonormality equalities removed from the SDP."""
+    res = _b.solve_batched(np.asarray(K, dtype=np.float64), pts_2d=_one(pts_2d, (2,)), pts_3d=_one(pts_3d, (3,)),
+                           eps=eps, max_iters=max_iters, variant="rc")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # rc.py has no optimality warning
+        return _unpack(res, verbose)

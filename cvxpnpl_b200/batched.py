@@ -60,11 +60,12 @@ class Workspace:
 
 
 def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1e-9, max_iters=2500,
-                  sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, return_Z=False, return_obj=True, workspace=None,
+                  sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, variant="full", return_Z=False, return_obj=True, workspace=None,
                   out: Optional[BatchedPoses] = None, device=None) -> BatchedPoses:
     """Solve B problems.  pts_2d [B,n,2], pts_3d [B,n,3], line_2d [B,m,2,2],
     line_3d [B,m,2,3], K [3,3] or [B,3,3]; any of the point / line pairs may be
-    omitted (PnP / PnL / PnPL: cvxpnpl.py:523-627)."""
+    omitted (PnP / PnL / PnPL: cvxpnpl.py:523-627).  variant="rc" solves the ablation
+    of benchmarks/toolkit/methods/rc.py (row-orthonormality equalities removed)."""
     _require_cuda()
     lib = _lib.load()
     if device is None:
@@ -130,6 +131,7 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.eps, d.max_iters, d.sweeps, d.rho_rel, d.alpha = float(eps), int(max_iters), int(sweeps), float(rho_rel), float(alpha)
         d.sigma = float(sigma)
         d.anderson = 0 if anderson else -1
+        d.variant = {"full": 0, "rc": 1}[variant]
         d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
         d.workspace, d.workspace_bytes = _ptr(workspace.buf), workspace.nbytes

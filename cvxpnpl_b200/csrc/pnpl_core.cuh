@@ -68,22 +68,24 @@ CVX_HD int sidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j 
 // ---- the 15 "triple" equalities (rows 2,3,5,8,9,11,13..21 of the reference's
 // A, cvxpnpl.py:401-435): sum_k s_k Z[i_k, j_k] = 0 over off-diagonal entries.
 // Each off-diagonal entry of Z belongs to exactly one triple.  (i > j always.)
-#define CVX_TRIPLES(X)                                     \
-    X(1, 0, +1, 4, 3, +1, 7, 6, +1)   /* r0.r1 */          \
-    X(2, 0, +1, 5, 3, +1, 8, 6, +1)   /* r0.r2 */          \
-    X(2, 1, +1, 5, 4, +1, 8, 7, +1)   /* r1.r2 */          \
-    X(3, 0, +1, 4, 1, +1, 5, 2, +1)   /* c0.c1 */          \
-    X(6, 0, +1, 7, 1, +1, 8, 2, +1)   /* c0.c2 */          \
-    X(6, 3, +1, 7, 4, +1, 8, 5, +1)   /* c1.c2 */          \
-    X(5, 1, +1, 4, 2, -1, 9, 6, -1)   /* (c0xc1)_0 = c2_0 */ \
-    X(3, 2, +1, 5, 0, -1, 9, 7, -1)                        \
-    X(4, 0, +1, 3, 1, -1, 9, 8, -1)                        \
-    X(8, 4, +1, 7, 5, -1, 9, 0, -1)   /* c1xc2 = c0 */     \
-    X(6, 5, +1, 8, 3, -1, 9, 1, -1)                        \
-    X(7, 3, +1, 6, 4, -1, 9, 2, -1)                        \
-    X(7, 2, +1, 8, 1, -1, 9, 3, -1)   /* c2xc0 = c1 */     \
-    X(8, 0, +1, 6, 2, -1, 9, 4, -1)                        \
-    X(6, 1, +1, 7, 0, -1, 9, 5, -1)
+// The last macro argument marks the three ROW-orthogonality triples, which (with the
+// three row-norm equalities) the "rc" ablation of benchmarks/toolkit/methods/rc.py drops.
+#define CVX_TRIPLES(X)                                        \
+    X(1, 0, +1, 4, 3, +1, 7, 6, +1, 1)   /* r0.r1 */          \
+    X(2, 0, +1, 5, 3, +1, 8, 6, +1, 1)   /* r0.r2 */          \
+    X(2, 1, +1, 5, 4, +1, 8, 7, +1, 1)   /* r1.r2 */          \
+    X(3, 0, +1, 4, 1, +1, 5, 2, +1, 0)   /* c0.c1 */          \
+    X(6, 0, +1, 7, 1, +1, 8, 2, +1, 0)   /* c0.c2 */          \
+    X(6, 3, +1, 7, 4, +1, 8, 5, +1, 0)   /* c1.c2 */          \
+    X(5, 1, +1, 4, 2, -1, 9, 6, -1, 0)   /* (c0xc1)_0 = c2_0 */ \
+    X(3, 2, +1, 5, 0, -1, 9, 7, -1, 0)                        \
+    X(4, 0, +1, 3, 1, -1, 9, 8, -1, 0)                        \
+    X(8, 4, +1, 7, 5, -1, 9, 0, -1, 0)   /* c1xc2 = c0 */     \
+    X(6, 5, +1, 8, 3, -1, 9, 1, -1, 0)                        \
+    X(7, 3, +1, 6, 4, -1, 9, 2, -1, 0)                        \
+    X(7, 2, +1, 8, 1, -1, 9, 3, -1, 0)   /* c2xc0 = c1 */     \
+    X(8, 0, +1, 6, 2, -1, 9, 4, -1, 0)                        \
+    X(6, 1, +1, 7, 0, -1, 9, 5, -1, 0)
 
 // ---------------------------------------------------------------------------------
 // Assembly: correspondences -> Q (45 unique entries of the 9x9 block, packed lower)
@@ -445,9 +447,13 @@ CVX_HD double jacobi_sweep(Arr<S> T, Arr<S> V)
 // under the congruence, Q' = Q (its last row/column is zero), Z'99 = sigma^2 and the
 // nine triples that touch row 9 pick up the coefficient 1/sigma on that entry.
 // sigma ~ 1.5 cuts the iteration count by a third on PnP/PnPL.
+//
+// rowk = 1 is the reference's SDP (22 equalities); rowk = 0 is the "rc" ablation of
+// benchmarks/toolkit/methods/rc.py:9-60 (the six row-orthonormality equalities removed).
 // ---------------------------------------------------------------------------------
 template <int S, class QR>
-CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, Arr<S> G, QR qr, double alpha, double isig, double z[55])
+CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, Arr<S> G, QR qr, double alpha, double isig, double rowk,
+                      double z[55])
 {
 #pragma unroll
     for (int e = 0; e < 55; ++e) z[e] = 0.0;
@@ -469,7 +475,7 @@ CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, Arr<S> G, QR qr, double alph
     double res = 0.0;
     const double inrm9 = 1.0 / (2.0 + isig * isig);
 #define CVX_Q(i, j) (((i) < 9 && (j) < 9) ? qr[sidx(i, j)] : 0.0)
-#define CVX_TRI(i0, j0, s0, i1, j1, s1, i2, j2, s2)                                         \
+#define CVX_TRI(i0, j0, s0, i1, j1, s1, i2, j2, s2, ROW)                                    \
     {                                                                                        \
         const int e0 = sidx(i0, j0), e1 = sidx(i1, j1), e2 = sidx(i2, j2);                  \
         const double m0 = M[e0], m1 = M[e1], m2 = M[e2];                                    \
@@ -478,7 +484,8 @@ CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, Arr<S> G, QR qr, double alph
         const double w2 = 2.0 * z[e2] - m2 - CVX_Q(i2, j2);                                 \
         /* third entry on the homogeneous row carries 1/sigma in the scaled problem */      \
         const double a2 = ((i2) == 9) ? (s2) * isig : (double)(s2);                         \
-        const double r = ((s0) * w0 + (s1) * w1 + a2 * w2) * (((i2) == 9) ? inrm9 : (1.0 / 3.0)); \
+        const double r = ((s0) * w0 + (s1) * w1 + a2 * w2) *                                 \
+                         (((i2) == 9) ? inrm9 : ((ROW) ? rowk * (1.0 / 3.0) : (1.0 / 3.0)));  \
         const double d0 = w0 - (s0) * r - z[e0];                                            \
         const double d1 = w1 - (s1) * r - z[e1];                                            \
         const double d2 = w2 - a2 * r - z[e2];                                              \
@@ -512,8 +519,9 @@ CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, Arr<S> G, QR qr, double alph
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const int i = 3 * c + r;
-                const double x = w[i] - (R[r] - 1.0) * (1.0 / 3.0) - (C[c] - 1.0) * (1.0 / 3.0)
-                                 + (Gs - 3.0) * (1.0 / 9.0);
+                // rowk = 0 ("rc" variant): only the column sums are constrained
+                const double x = w[i] - rowk * (R[r] - 1.0) * (1.0 / 3.0) - (C[c] - 1.0) * (1.0 / 3.0)
+                                 + rowk * (Gs - 3.0) * (1.0 / 9.0);
                 const double d = x - z[sidx(i, i)];
                 M[sidx(i, i)] = fma(alpha, d, md[i]);
                 G[sidx(i, i)] = alpha * d;

@@ -386,6 +386,7 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     o.sigma = d->sigma > 0 ? d->sigma : 1.5;
     o.anderson = d->anderson >= 0;
     o.aa_on2 = cvx::AA_RES2_ON;
+    o.rowk = (d->variant == 1) ? 0.0 : 1.0;
     o.max_iters = d->max_iters > 0 ? d->max_iters : 2500;
     o.sweeps = d->sweeps > 0 ? d->sweeps : 1;
     return o;

@@ -17,6 +17,7 @@ struct Opts {
     double sigma;     // homogeneous-coordinate scaling (see dr_step)
     bool anderson;    // Anderson acceleration of the DR iteration (see aa_step)
     double aa_on2;    // squared residual below which Anderson acceleration is active
+    double rowk;      // 1: reference SDP (22 equalities); 0: "rc" ablation (16 equalities)
 };
 
 struct Problem {
@@ -131,7 +132,7 @@ CVX_HD bool pass_dr(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT Q
 {
     if (!st.finite || !st.iterating) return false;
     double z[55];
-    const double res = dr_step(M, V, L, T, QR, o.alpha, 1.0 / o.sigma, z);
+    const double res = dr_step(M, V, L, T, QR, o.alpha, 1.0 / o.sigma, o.rowk, z);
     ++st.it;
 #if defined(CVX_TRACE) && !defined(__CUDA_ARCH__)
     printf("it %d res %.3e aa_mask %u\n", st.it, sqrt(res), st.aa.mask);

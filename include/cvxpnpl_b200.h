@@ -62,6 +62,9 @@ typedef struct cvxpnpl_b200_desc {
     double eps;             /* fixed-point residual tolerance; reference default 1e-9 */
     int32_t max_iters;      /* reference default 2500 */
     int32_t sweeps;         /* Jacobi sweeps per ADMM iteration (warm started); 0 = default */
+    int32_t variant;        /* 0: the reference's SDP (cvxpnpl.py:387-448); 1: "rc" ablation with the six
+                               row-orthonormality equalities removed (benchmarks/toolkit/methods/rc.py:9-60) */
+    int32_t reserved1;
     double rho_rel;         /* ADMM penalty = rho_rel * ||Q||_F ; 0 = default */
     double alpha;           /* over-relaxation in (0,2); 0 = default */
     double sigma;           /* homogeneous-coordinate scaling (preconditioner); 0 = default */

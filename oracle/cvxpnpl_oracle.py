@@ -111,6 +111,18 @@ def sdp_constraints():
 
 _A, _b = sdp_constraints()
 
+
+def sdp_constraints_rc():
+    """benchmarks/toolkit/methods/rc.py:9-60: the "rc" ablation drops the six row
+    orthonormality equalities (rows 1-6 of the full A: norms 1,4,6 and triples
+    2,3,5), leaving 16 equalities: A is 71 x 55."""
+    drop = [1, 2, 3, 4, 5, 6]
+    keep = [k for k in range(77) if k not in drop]
+    return _A[keep].copy(), _b[keep].copy()
+
+
+_A_rc, _b_rc = sdp_constraints_rc()
+
 # ----------------------------------------------------------------------------
 # constraint builders (cvxpnpl.py:20-153)
 # ----------------------------------------------------------------------------
@@ -307,9 +319,11 @@ def constraint_ortho_det(vecs, rank):
 # ----------------------------------------------------------------------------
 
 
-def solve_sdp(Q, eps=1e-9, max_iters=2500):
-    """cvxpnpl.py:478-492 with the scs call replaced by oracle/scs_port."""
-    res = scs_port.solve(_A, _b, vech10(Q, 2.0), eps_abs=eps, max_iters=max_iters)
+def solve_sdp(Q, eps=1e-9, max_iters=2500, variant="full"):
+    """cvxpnpl.py:478-492 (variant "full") or rc.py:86-96 (variant "rc") with the scs
+    call replaced by oracle/scs_port."""
+    A, b = (_A, _b) if variant == "full" else (_A_rc, _b_rc)
+    res = scs_port.solve(A, b, vech10(Q, 2.0), eps_abs=eps, max_iters=max_iters)
     info = dict(res["info"])
     info["y"] = res["y"]
     return vech10_inv(res["x"]), info
@@ -338,12 +352,13 @@ def extract(Z, A, B, dobj=None, eps=1e-9):
     return list(zip(Rt.transpose(0, 2, 1), t))
 
 
-def solve_relaxation(A, B, eps=1e-9, max_iters=2500, return_aux=False):
-    """cvxpnpl.py:454-520."""
+def solve_relaxation(A, B, eps=1e-9, max_iters=2500, return_aux=False, variant="full"):
+    """cvxpnpl.py:454-520; variant "rc" = rc.py:65-122 (same extraction, no
+    optimality warning)."""
     Q = np.zeros((10, 10))
     Q[:9, :9] = A.T @ A
-    Z, info = solve_sdp(Q, eps, max_iters)
-    poses = extract(Z, A, B, info["dobj"], eps)
+    Z, info = solve_sdp(Q, eps, max_iters, variant)
+    poses = extract(Z, A, B, info["dobj"] if variant == "full" else None, eps)
     if return_aux:
         return poses, {"Z": Z, "Q": Q, "info": info}
     return poses

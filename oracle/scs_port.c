@@ -32,14 +32,15 @@
 #include <string.h>
 
 #define N_ 55
-#define M_ 77
-#define NZ 22
+#define M_ 77   /* maximum number of rows: 22 equalities + 55 cone rows */
 #define PS 10
 
 typedef struct {
     double A[M_ * N_];      /* dense row-major */
     double b[M_];
     double L[N_ * N_];      /* Cholesky factor of I + A^T A (lower) */
+    int m;                  /* rows in use: nz + 55 */
+    int nz;                 /* equality (zero cone) rows: 22, or 16 for the "rc" ablation */
     int rp[M_ + 1];         /* CSR of A (the reference ships A sparse: csc_matrix, cvxpnpl.py:442) */
     int ci[M_ * N_];
     double cv[M_ * N_];
@@ -78,31 +79,36 @@ static void chol_solve55(const double *L, double *x)
 }
 
 /* one-time setup: stores A, b and factors I + A^T A */
-int scs_port_setup(const double *A, const double *b)
+int scs_port_setup(const double *A, const double *b, int nz)
 {
-    memcpy(W.A, A, sizeof(W.A));
-    memcpy(W.b, b, sizeof(W.b));
+    if (nz < 1 || nz + 55 > M_) return -1;
+    W.nz = nz;
+    W.m = nz + 55;
+    memset(W.A, 0, sizeof(W.A));
+    memset(W.b, 0, sizeof(W.b));
+    memcpy(W.A, A, sizeof(double) * W.m * N_);
+    memcpy(W.b, b, sizeof(double) * W.m);
     for (int i = 0; i < N_; ++i)
         for (int j = 0; j < N_; ++j) {
             double s = (i == j) ? 1.0 : 0.0;
-            for (int k = 0; k < M_; ++k) s += A[k * N_ + i] * A[k * N_ + j];
+            for (int k = 0; k < W.m; ++k) s += A[k * N_ + i] * A[k * N_ + j];
             W.L[i * N_ + j] = s;
         }
     chol55(W.L);
-    int nz = 0;
-    for (int k = 0; k < M_; ++k) {
-        W.rp[k] = nz;
+    int nnz = 0;
+    for (int k = 0; k < W.m; ++k) {
+        W.rp[k] = nnz;
         for (int j = 0; j < N_; ++j)
-            if (A[k * N_ + j] != 0.0) { W.ci[nz] = j; W.cv[nz] = A[k * N_ + j]; ++nz; }
+            if (A[k * N_ + j] != 0.0) { W.ci[nnz] = j; W.cv[nnz] = A[k * N_ + j]; ++nnz; }
     }
-    W.rp[M_] = nz;
+    W.rp[W.m] = nnz;
     W.ready = 1;
     return 0;
 }
 
 static void Amul(const double *x, double *y)      /* y = A x */
 {
-    for (int k = 0; k < M_; ++k) {
+    for (int k = 0; k < W.m; ++k) {
         double s = 0;
         for (int e = W.rp[k]; e < W.rp[k + 1]; ++e) s += W.cv[e] * x[W.ci[e]];
         y[k] = s;
@@ -111,7 +117,7 @@ static void Amul(const double *x, double *y)      /* y = A x */
 static void ATmul(const double *y, double *x)     /* x = A^T y */
 {
     for (int j = 0; j < N_; ++j) x[j] = 0;
-    for (int k = 0; k < M_; ++k) {
+    for (int k = 0; k < W.m; ++k) {
         const double yk = y[k];
         for (int e = W.rp[k]; e < W.rp[k + 1]; ++e) x[W.ci[e]] += W.cv[e] * yk;
     }
@@ -126,7 +132,7 @@ static void solveM(const double *wx, const double *wy, double *x, double *y)
     for (int j = 0; j < N_; ++j) x[j] = wx[j] - t[j];
     chol_solve55(W.L, x);
     Amul(x, y);
-    for (int k = 0; k < M_; ++k) y[k] += wy[k];
+    for (int k = 0; k < W.m; ++k) y[k] += wy[k];
 }
 
 /* Symmetric eigen-decomposition, PS x PS: Householder tridiagonalisation followed
@@ -287,7 +293,7 @@ int scs_port_solve(const double *c_in, double eps_abs, double eps_rel, int max_i
                    double *info)
 {
     if (!W.ready) return -100;
-    const int n = N_, m = M_, l = N_ + M_ + 1;
+    const int n = N_, m = W.m, l = N_ + W.m + 1;
     double u[N_ + M_ + 1], v[N_ + M_ + 1], ut[N_ + M_ + 1], w[N_ + M_ + 1];
     double hx[N_], hy[M_], gx[N_], gy[M_];   /* h = (c, b);  g = M^{-1} h */
     double x[N_], y[M_], s[M_], Ax[M_], ATy[N_];
@@ -330,7 +336,7 @@ int scs_port_solve(const double *c_in, double eps_abs, double eps_rel, int max_i
         for (int k = 0; k <= m; ++k) rel[k] = alpha * ut[n + k] + (1 - alpha) * u[n + k];
         for (int k = 0; k <= m; ++k) u[n + k] = rel[k] - v[n + k];
         /* y block: dual cone = R^22 x S_+^10 ; tau >= 0 */
-        proj_psd_svec(u + n + NZ);
+        proj_psd_svec(u + n + W.nz);
         if (u[l - 1] < 0) u[l - 1] = 0;
         /* --- dual update -------------------------------------------------- */
         for (int j = 0; j < n; ++j) v[j] = 0.0;  /* r = 0 for the free block */

@@ -31,7 +31,7 @@ def _load():
         build()
         lib = ctypes.CDLL(_SO)
         dp = ctypes.POINTER(ctypes.c_double)
-        lib.scs_port_setup.argtypes = [dp, dp]
+        lib.scs_port_setup.argtypes = [dp, dp, ctypes.c_int]
         lib.scs_port_setup.restype = ctypes.c_int
         lib.scs_port_solve.argtypes = [dp, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                        ctypes.c_double, ctypes.c_double, dp, dp, dp, dp]
@@ -48,16 +48,18 @@ _setup_key = None
 
 
 def solve(A, b, c, eps_abs=1e-9, eps_rel=0.0, max_iters=2500, alpha=1.5, cscale=10.0):
-    """min c'x s.t. Ax + s = b, s in {0}^22 x S_+^10 (A dense 77x55)."""
+    """min c'x s.t. Ax + s = b, s in {0}^nz x S_+^10 (A dense (nz+55) x 55; nz = 22, or 16 for
+    the "rc" ablation of benchmarks/toolkit/methods/rc.py)."""
     global _setup_key
     lib = _load()
     A = np.ascontiguousarray(A, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
     c = np.ascontiguousarray(c, dtype=np.float64)
-    assert A.shape == (77, 55) and b.shape == (77,) and c.shape == (55,)
+    m = A.shape[0]
+    assert A.shape == (m, 55) and b.shape == (m,) and c.shape == (55,) and m in (77, 71)
     key = (A.tobytes(), b.tobytes())
     if _setup_key != key:
-        lib.scs_port_setup(_p(A), _p(b))
+        assert lib.scs_port_setup(_p(A), _p(b), m - 55) == 0
         _setup_key = key
     x = np.empty(55)
     y = np.empty(77)
@@ -65,6 +67,7 @@ def solve(A, b, c, eps_abs=1e-9, eps_rel=0.0, max_iters=2500, alpha=1.5, cscale=
     info = np.empty(8)
     lib.scs_port_solve(_p(c), eps_abs, eps_rel, int(max_iters), alpha, cscale, _p(x), _p(y), _p(s), _p(info))
     status = {1: "solved", 2: "solved_inaccurate", -1: "infeasible_or_unbounded"}[int(info[6])]
+    y, s = y[:m], s[:m]
     return {
         "x": x, "y": y, "s": s,
         "info": {"pobj": info[0], "dobj": info[1], "res_pri": info[2], "res_dual": info[3],

@@ -30,8 +30,11 @@ from oracle import scs_port as _port  # noqa: E402
 __version__ = "3.2.0"
 
 
-def solve(data, cone, eps_abs=1e-9, eps_rel=0.0, max_iters=2500, verbose=False, **kw):
-    assert cone.get("z", cone.get("f")) == 22 and list(cone["s"]) == [10]
+def solve(data, cone, eps_abs=1e-9, eps_rel=0.0, max_iters=2500, verbose=False, eps=None, **kw):
+    # `eps=` is the SCS 2.x spelling still used by benchmarks/toolkit/methods/rc.py:90-96
+    if eps is not None:
+        eps_abs = eps
+    assert cone.get("z", cone.get("f")) in (22, 16) and list(cone["s"]) == [10]
     A = data["A"]
     A = A.toarray() if hasattr(A, "toarray") else np.asarray(A)
     mi = int(os.environ.get("ORACLE_SCS_MAX_ITERS", max_iters))

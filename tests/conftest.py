@@ -19,4 +19,4 @@ def golden():
     import numpy as np
 
     return {name: np.load(os.path.join(GOLDEN, name + ".npz"))
-            for name in ("units", "examples", "synth", "degenerate")}
+            for name in ("units", "examples", "synth", "degenerate", "rc")}

@@ -14,6 +14,7 @@ What each file pins:
   synth.npz     seeded synthetic PnP-8 / PnPL-8+4 / PnL-6 problems (noise 0,1,2 px):
                 inputs, the reference's A and B, and the poses the reference
                 returns (SDP solved by the shim to eps_abs 1e-9, fully converged).
+  rc.npz        the "rc" ablation (benchmarks/toolkit/methods/rc.py): static data + poses.
   degenerate.npz minimal / planar configurations that take the rank-2 / rank-4
                 branches: inputs, Z returned by the shim, and the reference's
                 candidate poses for that Z.
@@ -207,7 +208,25 @@ def degenerate_set():
     np.savez(os.path.join(OUT, "degenerate.npz"), **out)
 
 
+def rc_set():
+    """benchmarks/toolkit/methods/rc.py (the 16-equality ablation) run verbatim: its static
+    data and its poses on seeded PnP-8 problems."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_rc", "/root/reference/benchmarks/toolkit/methods/rc.py")
+    rcm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rcm)
+    d = synth.make_batch(6, 8, 0, noise=1.0, seed=2100)
+    Rs, ts, ns = [], [], []
+    for i in range(6):
+        A, Bm = _ref_AB(d, i, 8, 0)
+        R, t, n = pack_poses(rcm._solve_relaxation_rc(A, Bm))
+        Rs.append(R), ts.append(t), ns.append(n)
+    np.savez(os.path.join(OUT, "rc.npz"), A_rc=rcm._A_rc.toarray(), b_rc=rcm._b_rc, K=d["K"], pts_2d=d["pts_2d"],
+             pts_3d=d["pts_3d"], R=np.array(Rs), t=np.array(ts), n=np.array(ns))
+
+
 if __name__ == "__main__":
+    rc_set()
     units()
     examples()
     synth_set()

@@ -13,7 +13,7 @@
 extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
                           const double* pts_2d, const double* pts_3d, const double* line_2d,
                           const double* line_3d, double eps, int max_iters, int sweeps, double rho_rel,
-                          double alpha, double sigma, int anderson, double* R, double* t, int32_t* n_poses, int32_t* status,
+                          double alpha, double sigma, int anderson, int variant, double* R, double* t, int32_t* n_poses, int32_t* status,
                           int32_t* iters, double* obj, double* Z)
 {
     cvx::Opts o;
@@ -24,6 +24,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
     o.sweeps = sweeps > 0 ? sweeps : 1;
     o.sigma = sigma > 0 ? sigma : 1.5;
     o.anderson = anderson != 0;
+    o.rowk = variant == 1 ? 0.0 : 1.0;
     o.aa_on2 = (anderson > 1) ? (1e-3 * anderson) * (1e-3 * anderson) : cvx::AA_RES2_ON;   // test hook: threshold in 1e-3 units
     std::vector<double> V(100), M(56), T(56), L(10), qr(45);   // T[55] = 0: zero pad for aa_step
     std::vector<float> hist(cvx::AA_WORDS);

@@ -330,3 +330,18 @@ def test_batched_synth_suite(cb):
     assert cell.ang_median_deg < 2.0 and cell.failed < 0.01
     cell = suite.run_cell("pnl", 4, 0.0, 2000, seed=3)          # minimal-ish: several candidates
     assert cell.multi > 0.05 and cell.ang_median_deg < 1e-3
+
+
+def test_rc_variant(cb, golden):
+    """the "rc" operator (benchmarks/toolkit/methods/rc.py, six row
+    orthonormality equalities removed) against the verbatim reference's poses."""
+    from cvxpnpl_b200 import synth
+    g = golden["rc"]
+    res = cb.solve_batched(g["K"], pts_2d=g["pts_2d"], pts_3d=g["pts_3d"], variant="rc")
+    torch.cuda.synchronize()
+    assert (res.n_poses.cpu().numpy() == g["n"]).all() and ((res.status & 0xFF) == 0).all()
+    R, t = res.R.cpu().numpy()[:, 0], res.t.cpu().numpy()[:, 0]
+    assert synth.rotation_angle(g["R"][:, 0], R).max() < ROT_TOL
+    assert (np.linalg.norm(t - g["t"][:, 0], axis=1) / np.linalg.norm(g["t"][:, 0], axis=1)).max() < T_TOL
+    poses = cb.rc(g["pts_2d"][0], g["pts_3d"][0], g["K"])
+    assert len(poses) == 1 and synth.rotation_angle(g["R"][0, 0], poses[0][0]) < ROT_TOL

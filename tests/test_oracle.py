@@ -124,3 +124,18 @@ def test_degenerate_extraction(golden, name):
         dist = np.sort(np.abs(got[:, None, :] - exp[None, :, :]).max(-1).min(1))
         assert dist[(n - 1) // 2] < 1e-6
         assert np.all(dist[: max(n - 1, 1)] < 1e-4)
+
+
+def test_rc_variant_against_reference(golden):
+    """benchmarks/toolkit/methods/rc.py: static data and poses of the verbatim reference."""
+    g = golden["rc"]
+    assert np.array_equal(orc._A_rc, g["A_rc"]) and np.array_equal(orc._b_rc, g["b_rc"])
+    for i in range(3):
+        C, N = orc.point_constraints(g["pts_2d"][i], g["pts_3d"][i], g["K"])
+        A, B = orc.reduce_translation(C, N)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            poses = orc.solve_relaxation(A, B, max_iters=200000, variant="rc")
+        assert len(poses) == int(g["n"][i]) == 1
+        assert synth.rotation_angle(g["R"][i, 0], poses[0][0]) < 1e-6
+        assert np.linalg.norm(poses[0][1] - g["t"][i, 0]) / np.linalg.norm(g["t"][i, 0]) < 1e-6
