@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--noise", type=float, default=1.0, help="pixel noise sigma (synth.py grid: 0,1,2)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--large-n", type=int, default=0,
+                    help="side measurement (not the headline): HBM roofline of the streaming assembly with this "
+                         "many points per problem (benchmarks/scalability/pnp.py regime)")
     return ap.parse_args()
 
 
@@ -359,9 +362,40 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_large_n(a):
+    """Achieved HBM bandwidth of the large-n assembly (40 B per point streamed once)."""
+    import torch
+    import cvxpnpl_b200 as cb
+    from cvxpnpl_b200 import synth
+    n, B = a.large_n, max(1, min(65535, int(2e9 // (40 * a.large_n))))   # ~2 GB of correspondences (> L2)
+    dev = torch.device("cuda", 0)
+    d = synth.make_batch(B, n, 0, noise=1.0, seed=1)
+    p2, p3, K = (torch.from_numpy(d[k]).to(dev) for k in ("pts_2d", "pts_3d", "K"))
+    for _ in range(3):
+        cb.assemble_batched(K, p2, p3)
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(a.steps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        cb.assemble_batched(K, p2, p3)
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ms = sum(s.elapsed_time(e) for s, e in evs) / a.steps
+    peaks, kind = measured_peaks()
+    gbs = 40.0 * n * B / (ms * 1e-3) / 1e9
+    print(json.dumps({"metric": "large-n assembly", "points_per_problem": n, "problems": B, "ms": ms,
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": gbs / peaks["hbm_gbs"], "peak_kind": kind,
+                                   "algorithmic_bytes_per_point": 40}}))
+
+
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
+    if args.large_n:
+        run_large_n(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

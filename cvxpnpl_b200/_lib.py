@@ -58,6 +58,7 @@ EXPORTS = (
     "cvxpnpl_b200_extract",
     "cvxpnpl_b200_last_launch_count",
     "cvxpnpl_b200_fp64_probe",
+    "cvxpnpl_b200_null",
 )
 
 _lib = None
@@ -91,6 +92,8 @@ def load():
     lib.cvxpnpl_b200_extract.restype = ctypes.c_int
     lib.cvxpnpl_b200_extract.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p]
+    lib.cvxpnpl_b200_null.restype = ctypes.c_int
+    lib.cvxpnpl_b200_null.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p]
     lib.cvxpnpl_b200_last_launch_count.restype = ctypes.c_int
     lib.cvxpnpl_b200_fp64_probe.restype = ctypes.c_int
     lib.cvxpnpl_b200_fp64_probe.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,

@@ -13,6 +13,8 @@ import torch
 from . import _lib
 
 ST_OK, ST_MAX_ITERS, ST_NAN, ST_SINGULAR, ST_RANK0 = 0, 1, 2, 3, 4
+#: correspondences per problem from which the streaming (bandwidth-bound) assembly is used
+LARGE_N = 256
 ST_CODE_MASK = 0xFF
 FLAG_NOT_CERTIFIED = 0x100
 
@@ -105,6 +107,23 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
     if k_batched and K.shape[0] != B:
         raise ValueError("batched K must be [B,3,3]")
 
+    n_corr = (pts_2d.shape[1] if have_p else 0) + (line_2d.shape[1] if have_l else 0)
+    if n_corr >= LARGE_N and B > 0:
+        # many correspondences per problem (benchmarks/scalability/pnp.py:37-40): the
+        # assembly is a bandwidth-bound streaming reduction with its own kernels; the
+        # SDP and the extraction then run as stages on the [B,9,9] / [B,10,10] matrices
+        with torch.cuda.device(device):
+            Q, Bm = assemble_batched(K, pts_2d if have_p else None, pts_3d if have_p else None,
+                                     line_2d if have_l else None, line_3d if have_l else None)
+            Z, dobj, iters, status = solve_sdp_batched(Q, eps=eps, max_iters=max_iters, sweeps=sweeps, rho_rel=rho_rel,
+                                                       alpha=alpha, sigma=sigma, anderson=anderson)
+            res = extract_batched(Z, Q, Bm, dobj, eps=eps)
+            res.iters = iters
+            # keep the solver's status (MAX_ITERS / NaN) where extraction itself succeeded
+            res.status = torch.where((res.status & ST_CODE_MASK) == ST_OK, res.status | status, res.status)
+            res.Z = Z if return_Z else None
+            res.launches = 4
+        return res
     with torch.cuda.device(device):
         if out is None:
             out = BatchedPoses(
@@ -231,6 +250,32 @@ def extract_batched(Z, Q, Bmat, dobj=None, eps=1e-9) -> BatchedPoses:
         dobj = _dev_f64(dobj, device, (), "dobj")
     stream = torch.cuda.current_stream(device).cuda_stream
     _lib.check(lib.cvxpnpl_b200_extract(ctypes.byref(d), _ptr(Z), _ptr(Q), _ptr(Bmat), _ptr(dobj), ctypes.c_void_p(stream)))
+    return out
+
+
+def null_batched(pts_2d, pts_3d, K) -> BatchedPoses:
+    """Batched "null" baseline (benchmarks/toolkit/methods/pnp.py:24-55): no SDP, the
+    smallest right singular vector of A projected onto SO(3)."""
+    _require_cuda()
+    lib = _lib.load()
+    device = torch.device("cuda", torch.cuda.current_device())
+    pts_2d, pts_3d = _dev_f64(pts_2d, device, (2,), "pts_2d"), _dev_f64(pts_3d, device, (3,), "pts_3d")
+    K = _dev_f64(K, device, (3, 3), "K")
+    B = pts_2d.shape[0]
+    out = BatchedPoses(
+        R=torch.empty((B, 4, 3, 3), dtype=torch.float64, device=device),
+        t=torch.empty((B, 4, 3), dtype=torch.float64, device=device),
+        n_poses=torch.empty(B, dtype=torch.int32, device=device),
+        status=torch.empty(B, dtype=torch.int32, device=device),
+        iters=torch.zeros(B, dtype=torch.int32, device=device),
+    )
+    d = _lib.Desc()
+    d.batch, d.n_pts, d.n_lines, d.k_batched = B, pts_2d.shape[1], 0, int(K.dim() == 3)
+    d.K, d.pts_2d, d.pts_3d = _ptr(K), _ptr(pts_2d), _ptr(pts_3d)
+    d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    _lib.check(lib.cvxpnpl_b200_null(ctypes.byref(d), ctypes.c_void_p(stream)))
+    out.launches = int(lib.cvxpnpl_b200_last_launch_count())
     return out
 
 

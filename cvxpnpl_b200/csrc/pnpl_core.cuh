@@ -157,42 +157,10 @@ CVX_HD void bearing(const double Ki[9], double u, double v, double p[3])
     p[2] = fma(Ki[6], u, fma(Ki[7], v, Ki[8]));
 }
 
-// Q: 45 packed (9x9 lower, row-major), Bm: 27 (3x9 row-major).  Generic output
-// accessors so the caller can target registers, shared or global memory.
-// Returns false if the 3x3 normal system is singular / data non-finite.
+// From the accumulated sums to B = (N'N)^-1 N'C and Q = C'C - (N'C)' B.
 template <class QOut, class BOut>
-CVX_HD bool assemble(const double* K, const double* pts_2d, const double* pts_3d, int n_pts,
-                     const double* line_2d, const double* line_3d, int n_lines, QOut Q, BOut Bm)
+CVX_HD bool reduce_accum(const Accum& acc, QOut Q, BOut Bm)
 {
-    double Kl[9], Ki[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Kl[i] = K[i];
-    inv3(Kl, Ki);
-
-    Accum acc;
-    accum_init(acc);
-    for (int i = 0; i < n_pts; ++i) {
-        double p[3], P[3] = {pts_3d[3 * i], pts_3d[3 * i + 1], pts_3d[3 * i + 2]};
-        bearing(Ki, pts_2d[2 * i], pts_2d[2 * i + 1], p);
-        double n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
-        double W[6] = {n2 - p[0] * p[0], -p[1] * p[0], n2 - p[1] * p[1],
-                       -p[2] * p[0],     -p[2] * p[1], n2 - p[2] * p[2]};
-        accum_add(acc, P, W);
-    }
-    for (int i = 0; i < n_lines; ++i) {
-        double a[3], b[3];
-        bearing(Ki, line_2d[4 * i], line_2d[4 * i + 1], a);
-        bearing(Ki, line_2d[4 * i + 2], line_2d[4 * i + 3], b);
-        double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
-        double inv = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-        n[0] *= inv; n[1] *= inv; n[2] *= inv;
-        double W[6] = {n[0] * n[0], n[1] * n[0], n[1] * n[1], n[2] * n[0], n[2] * n[1], n[2] * n[2]};
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            double P[3] = {line_3d[6 * i + 3 * e], line_3d[6 * i + 3 * e + 1], line_3d[6 * i + 3 * e + 2]};
-            accum_add(acc, P, W);
-        }
-    }
     // inverse of the symmetric 3x3 N'N
     double G[9] = {acc.W[0], acc.W[1], acc.W[3], acc.W[1], acc.W[2], acc.W[4], acc.W[3], acc.W[4], acc.W[5]};
     double Gi[9];
@@ -229,6 +197,45 @@ CVX_HD bool assemble(const double* K, const double* pts_2d, const double* pts_3d
         ok = ok && isfinite(Bl[i]);
     }
     return ok;
+}
+
+// Q: 45 packed (9x9 lower, row-major), Bm: 27 (3x9 row-major).  Generic output
+// accessors so the caller can target registers, shared or global memory.
+// Returns false if the 3x3 normal system is singular / data non-finite.
+template <class QOut, class BOut>
+CVX_HD bool assemble(const double* K, const double* pts_2d, const double* pts_3d, int n_pts,
+                     const double* line_2d, const double* line_3d, int n_lines, QOut Q, BOut Bm)
+{
+    double Kl[9], Ki[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Kl[i] = K[i];
+    inv3(Kl, Ki);
+
+    Accum acc;
+    accum_init(acc);
+    for (int i = 0; i < n_pts; ++i) {
+        double p[3], P[3] = {pts_3d[3 * i], pts_3d[3 * i + 1], pts_3d[3 * i + 2]};
+        bearing(Ki, pts_2d[2 * i], pts_2d[2 * i + 1], p);
+        double n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        double W[6] = {n2 - p[0] * p[0], -p[1] * p[0], n2 - p[1] * p[1],
+                       -p[2] * p[0],     -p[2] * p[1], n2 - p[2] * p[2]};
+        accum_add(acc, P, W);
+    }
+    for (int i = 0; i < n_lines; ++i) {
+        double a[3], b[3];
+        bearing(Ki, line_2d[4 * i], line_2d[4 * i + 1], a);
+        bearing(Ki, line_2d[4 * i + 2], line_2d[4 * i + 3], b);
+        double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        double inv = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        n[0] *= inv; n[1] *= inv; n[2] *= inv;
+        double W[6] = {n[0] * n[0], n[1] * n[0], n[1] * n[1], n[2] * n[0], n[2] * n[1], n[2] * n[2]};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double P[3] = {line_3d[6 * i + 3 * e], line_3d[6 * i + 3 * e + 1], line_3d[6 * i + 3 * e + 2]};
+            accum_add(acc, P, W);
+        }
+    }
+    return reduce_accum(acc, Q, Bm);
 }
 
 // ---------------------------------------------------------------------------------

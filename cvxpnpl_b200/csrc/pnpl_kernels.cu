@@ -220,6 +220,163 @@ __global__ void __launch_bounds__(NT_F) finish_kernel(cvxpnpl_b200_desc d, Opts 
 }
 
 // ---------------------------------------------------------------------------------
+// "null" baseline (benchmarks/toolkit/methods/pnp.py:24-55): no SDP -- the smallest
+// right singular vector of A (= smallest eigenvector of Q = A'A), projected onto
+// O(3) by SVD, sign fixed to det +1, t = -B r.  One thread per problem.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT_F) null_kernel(cvxpnpl_b200_desc d)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * NT_F + tid;
+    if (b >= d.batch) return;
+    cvx::Arr<NT_F> V{smem + tid};
+    cvx::Arr<NT_F> Qs{smem + (size_t)100 * NT_F + tid};
+    cvx::Arr<NT_F> Bs{smem + (size_t)145 * NT_F + tid};
+    cvx::Arr<NT_F> T{smem + (size_t)172 * NT_F + tid};   // 55
+    const cvx::Problem pr = problem_at(d, b);
+    const bool finite = cvx::assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
+    double tr = 0;
+    for (int i = 0; i < 9; ++i) tr += Qs[cvx::sidx(i, i)];
+    for (int i = 0; i < 10; ++i) {
+        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
+        for (int j = 0; j <= i; ++j) T[cvx::sidx(i, j)] = (i < 9) ? Qs[cvx::sidx(i, j)] : ((j == 9) ? 1e3 * (tr + 1.0) : 0.0);
+    }
+    for (int s = 0; s < 40; ++s) {
+        double dg = 0;
+        for (int j = 0; j < 10; ++j) dg = fma(T[cvx::sidx(j, j)], T[cvx::sidx(j, j)], dg);
+        if (!(cvx::jacobi_sweep(T, V) > 1e-32 * dg)) break;
+    }
+    int jmin = 0;
+    double lmin = 1e300;
+    for (int j = 0; j < 10; ++j) {
+        const double l = T[cvx::sidx(j, j)];
+        // the padded direction has a zero in rows 0..8 of its eigenvector: skip it
+        if (fabs(V[90 + j]) < 0.5 && l < lmin) { lmin = l; jmin = j; }
+    }
+    double rc[9], Rm[9], tv[3];
+    for (int i = 0; i < 9; ++i) rc[i] = V[i * 10 + jmin];
+    cvx::finish_pose(rc, Qs, Bs, Rm, tv);
+    // sign fix: R *= sign(det R) (pnp.py:53); t = -B vec(R) flips with it
+    const double det = Rm[0] * (Rm[4] * Rm[8] - Rm[5] * Rm[7]) - Rm[1] * (Rm[3] * Rm[8] - Rm[5] * Rm[6]) +
+                       Rm[2] * (Rm[3] * Rm[7] - Rm[4] * Rm[6]);
+    const double sg = (det < 0) ? -1.0 : 1.0;
+    double* Ro = d.R + b * 36;
+    double* to = d.t + b * 12;
+    for (int i = 0; i < 36; ++i) Ro[i] = nan("");
+    for (int i = 0; i < 12; ++i) to[i] = nan("");
+    for (int i = 0; i < 9; ++i) Ro[i] = finite ? sg * Rm[i] : nan("");
+    for (int i = 0; i < 3; ++i) to[i] = finite ? sg * tv[i] : nan("");
+    d.n_poses[b] = 1;
+    d.status[b] = finite ? cvx::ST_OK : cvx::ST_NAN;
+    if (d.iters) d.iters[b] = 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Large-n assembly (benchmarks/scalability/pnp.py:37-40 sweeps n up to 10 000): the
+// only regime where the path is bandwidth bound (40 B per point streamed once).  A
+// problem's correspondences are split into chunks; each CTA accumulates the 60
+// Kronecker sums (P P' (x) W: 36, P' (x) W: 18, W: 6) of its chunk in registers,
+// reduces them with warp shuffles + shared memory and adds them to the problem's
+// accumulator with 60 atomics; a second kernel turns the sums into Q and B.
+// The accumulators live in the caller's Q buffer (81 >= 60 doubles per problem).
+// ---------------------------------------------------------------------------------
+constexpr int NT_L = 256;
+constexpr int LARGE_N = 256;          // correspondences per problem from which this path is used
+constexpr int CHUNK_ELEMS = 4096;     // correspondences per CTA
+
+__global__ void __launch_bounds__(NT_L) accumulate_kernel(cvxpnpl_b200_desc d, double* acc_out)
+{
+    __shared__ double red[NT_L / 32][60];
+    const int64_t b = blockIdx.y;
+    const int n_total = d.n_pts + d.n_lines;
+    const int lo = blockIdx.x * CHUNK_ELEMS;
+    const int hi = min(lo + CHUNK_ELEMS, n_total);
+    const double* K = problem_K(d, b);
+    double Kl[9], Ki[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Kl[i] = K[i];
+    cvx::inv3(Kl, Ki);
+    cvx::Accum acc;
+    cvx::accum_init(acc);
+    const double* p2 = d.pts_2d + b * 2 * (int64_t)d.n_pts;
+    const double* p3 = d.pts_3d + b * 3 * (int64_t)d.n_pts;
+    const double* l2 = d.line_2d + b * 4 * (int64_t)d.n_lines;
+    const double* l3 = d.line_3d + b * 6 * (int64_t)d.n_lines;
+    for (int e = lo + threadIdx.x; e < hi; e += NT_L) {
+        if (e < d.n_pts) {
+            double p[3], P[3] = {p3[3 * e], p3[3 * e + 1], p3[3 * e + 2]};
+            cvx::bearing(Ki, p2[2 * e], p2[2 * e + 1], p);
+            const double n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+            const double W[6] = {n2 - p[0] * p[0], -p[1] * p[0], n2 - p[1] * p[1],
+                                 -p[2] * p[0],     -p[2] * p[1], n2 - p[2] * p[2]};
+            cvx::accum_add(acc, P, W);
+        } else {
+            const int i = e - d.n_pts;
+            double a[3], c[3];
+            cvx::bearing(Ki, l2[4 * i], l2[4 * i + 1], a);
+            cvx::bearing(Ki, l2[4 * i + 2], l2[4 * i + 3], c);
+            double n[3] = {a[1] * c[2] - a[2] * c[1], a[2] * c[0] - a[0] * c[2], a[0] * c[1] - a[1] * c[0]};
+            const double inv = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            n[0] *= inv; n[1] *= inv; n[2] *= inv;
+            const double W[6] = {n[0] * n[0], n[1] * n[0], n[1] * n[1], n[2] * n[0], n[2] * n[1], n[2] * n[2]};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const double P[3] = {l3[6 * i + 3 * q], l3[6 * i + 3 * q + 1], l3[6 * i + 3 * q + 2]};
+                cvx::accum_add(acc, P, W);
+            }
+        }
+    }
+    // flatten, warp-reduce, CTA-reduce, one atomic per sum
+    double v[60];
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) v[6 * g + e] = acc.PPW[g][e];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) v[36 + 6 * g + e] = acc.PW[g][e];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) v[54 + e] = acc.W[e];
+#pragma unroll
+    for (int k = 0; k < 60; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 60; ++k) red[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 60) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < NT_L / 32; ++w) s += red[w][threadIdx.x];
+        atomicAdd(acc_out + b * 81 + threadIdx.x, s);
+    }
+}
+
+__global__ void finalize_kernel(cvxpnpl_b200_desc d, double* Q, double* Bmat)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.batch) return;
+    cvx::Accum acc;
+    const double* a = Q + b * 81;
+    for (int g = 0; g < 6; ++g)
+        for (int e = 0; e < 6; ++e) acc.PPW[g][e] = a[6 * g + e];
+    for (int g = 0; g < 3; ++g)
+        for (int e = 0; e < 6; ++e) acc.PW[g][e] = a[36 + 6 * g + e];
+    for (int e = 0; e < 6; ++e) acc.W[e] = a[54 + e];
+    double q[45], bm[27];
+    cvx::reduce_accum(acc, q, bm);
+    double* Qo = Q + b * 81;
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) Qo[9 * i + j] = q[cvx::sidx(i, j)];
+    for (int i = 0; i < 27; ++i) Bmat[b * 27 + i] = bm[i];
+}
+
+// ---------------------------------------------------------------------------------
 // Stage kernels (parity testing of the individual reference functions)
 // ---------------------------------------------------------------------------------
 __global__ void assemble_kernel(cvxpnpl_b200_desc d, double* Q, double* Bmat)
@@ -476,6 +633,29 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     return 0;
 }
 
+int cvxpnpl_b200_null(const cvxpnpl_b200_desc* d, void* stream)
+{
+    g_launches = 0;
+    if (int rc = check_common(d)) return rc;
+    if (d->batch == 0) return 0;
+    if (d->n_pts + d->n_lines <= 0) return fail(-4, "no correspondences");
+    if (!d->K || (d->n_pts && (!d->pts_2d || !d->pts_3d)) || (d->n_lines && (!d->line_2d || !d->line_3d)))
+        return fail(-5, "null input pointer");
+    if (!d->R || !d->t || !d->n_poses || !d->status) return fail(-6, "null output pointer");
+    const size_t smem = (size_t)NT_F * 227 * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(null_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    null_kernel<<<(unsigned)((d->batch + NT_F - 1) / NT_F), NT_F, smem, (cudaStream_t)stream>>>(*d);
+    g_launches = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
 int cvxpnpl_b200_fp64_probe(double* out, int64_t out_len, int iters, int64_t* flops, void* stream)
 {
     g_launches = 0;
@@ -500,6 +680,19 @@ int cvxpnpl_b200_assemble(const cvxpnpl_b200_desc* d, double* Q, double* Bmat, v
     if (d->batch == 0) return 0;
     if (!Q || !Bmat || !d->K) return fail(-5, "null pointer");
     if (d->n_pts + d->n_lines <= 0) return fail(-4, "no correspondences");
+    if (d->n_pts + d->n_lines >= LARGE_N) {
+        // bandwidth-bound regime: chunked streaming reduction (3 operations on the stream)
+        cudaError_t e0 = cudaMemsetAsync(Q, 0, (size_t)d->batch * 81 * sizeof(double), (cudaStream_t)stream);
+        if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
+        const int chunks = (d->n_pts + d->n_lines + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
+        if (d->batch > 65535) return fail(-8, "large-n assembly supports at most 65535 problems per call");
+        accumulate_kernel<<<dim3((unsigned)chunks, (unsigned)d->batch), NT_L, 0, (cudaStream_t)stream>>>(*d, Q);
+        finalize_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*d, Q, Bmat);
+        g_launches = 2;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+        return 0;
+    }
     const int64_t blocks = (d->batch + 127) / 128;
     assemble_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*d, Q, Bmat);
     g_launches = 1;

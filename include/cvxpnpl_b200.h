@@ -108,6 +108,11 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* desc, const double* Q, void*
 int cvxpnpl_b200_extract(const cvxpnpl_b200_desc* desc, const double* Z, const double* Q,
                          const double* Bmat, const double* dobj, void* stream);
 
+/* The "null" baseline of benchmarks/toolkit/methods/pnp.py:24-55 (no SDP: smallest
+ * right singular vector of A, SVD projection, det sign fix).  Writes candidate 0 of
+ * desc->R / desc->t, n_poses = 1, status. */
+int cvxpnpl_b200_null(const cvxpnpl_b200_desc* desc, void* stream);
+
 /* Measurement aid (no reference counterpart): launches an FP64 FMA throughput
  * probe; `out` needs (#SMs * 8 * 256) doubles, *flops receives the flop count of
  * the launch.  bench.py times it with CUDA events to obtain the fp64 peak it

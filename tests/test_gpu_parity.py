@@ -345,3 +345,51 @@ def test_rc_variant(cb, golden):
     assert (np.linalg.norm(t - g["t"][:, 0], axis=1) / np.linalg.norm(g["t"][:, 0], axis=1)).max() < T_TOL
     poses = cb.rc(g["pts_2d"][0], g["pts_3d"][0], g["K"])
     assert len(poses) == 1 and synth.rotation_angle(g["R"][0, 0], poses[0][0]) < ROT_TOL
+
+
+def test_null_baseline(cb):
+    """benchmarks/toolkit/methods/pnp.py:24-55 restated in numpy
+    (smallest right singular vector of A, SVD projection, det sign fix, t = -B r)."""
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    d = synth.make_batch(50, 8, 0, noise=1.0, seed=41)
+    res = cb.null_batched(d["pts_2d"], d["pts_3d"], d["K"])
+    torch.cuda.synchronize()
+    R, t = res.R.cpu().numpy()[:, 0], res.t.cpu().numpy()[:, 0]
+    for i in range(50):
+        C, N = orc.point_constraints(d["pts_2d"][i], d["pts_3d"][i], d["K"])
+        A, B = orc.reduce_translation(C, N)
+        Rn = np.linalg.svd(A)[2][-1].reshape((3, 3)).T
+        U, _, Vt = np.linalg.svd(Rn)
+        Rn = U @ Vt
+        Rn *= np.sign(np.linalg.det(Rn))
+        tn = -B @ Rn.ravel("F")
+        assert synth.rotation_angle(Rn, R[i]) < 1e-7, i
+        assert np.linalg.norm(tn - t[i]) / np.linalg.norm(tn) < 1e-7, i
+
+
+def test_large_n_assembly(cb):
+    """SURVEY 8f rank 3 (benchmarks/scalability/pnp.py:37-40, n up to 10 000): the
+    chunked streaming assembly against the oracle's A'A and B, and the full path
+    against ground truth."""
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    for n_pts, n_lines in ((1000, 0), (5000, 300), (0, 9000)):
+        d = synth.make_batch(3, n_pts, n_lines, noise=1.0, seed=51)
+        Q, Bm = cb.assemble_batched(d["K"], d["pts_2d"] if n_pts else None, d["pts_3d"] if n_pts else None,
+                                    d["line_2d"] if n_lines else None, d["line_3d"] if n_lines else None)
+        torch.cuda.synchronize()
+        for i in range(3):
+            C, N = orc._stack(d["pts_2d"][i] if n_pts else None, d["pts_3d"][i] if n_pts else None,
+                              d["line_2d"][i] if n_lines else None, d["line_3d"][i] if n_lines else None, d["K"])
+            A, B = orc.reduce_translation(C, N)
+            ref = A.T @ A
+            assert np.abs(Q[i].cpu().numpy() - ref).max() < 1e-11 * np.abs(ref).max()
+            assert np.allclose(Bm[i].cpu().numpy(), B, rtol=1e-9, atol=1e-11)
+    d = synth.make_batch(40, 2000, 0, noise=1.0, seed=52)
+    res = _solve(cb, d, 2000, 0)
+    assert ((res.status & 0xFF) == 0).all() and (res.n_poses == 1).all()
+    ang, terr = synth.pose_error(d["R_gt"], d["t_gt"], res.R[:, 0].cpu().numpy(), res.t[:, 0].cpu().numpy())
+    assert ang.max() < 2e-3 and terr.max() < 2e-3      # 2000 points average the 1 px noise down
+    poses = cb.pnp(d["pts_2d"][0], d["pts_3d"][0], d["K"])
+    assert len(poses) == 1 and synth.rotation_angle(poses[0][0], res.R[0, 0].cpu().numpy()) < 1e-9
