@@ -303,15 +303,31 @@ __global__ void __launch_bounds__(NT_L) accumulate_kernel(cvxpnpl_b200_desc d, d
     const double* p3 = d.pts_3d + b * 3 * (int64_t)d.n_pts;
     const double* l2 = d.line_2d + b * 4 * (int64_t)d.n_lines;
     const double* l3 = d.line_3d + b * 6 * (int64_t)d.n_lines;
-    for (int e = lo + threadIdx.x; e < hi; e += NT_L) {
-        if (e < d.n_pts) {
-            double p[3], P[3] = {p3[3 * e], p3[3 * e + 1], p3[3 * e + 2]};
-            cvx::bearing(Ki, p2[2 * e], p2[2 * e + 1], p);
+    // points: four per thread in flight (all loads issued before the arithmetic)
+    const int hi_p = min(hi, d.n_pts);
+    for (int e0 = lo + threadIdx.x; e0 < hi_p; e0 += 4 * NT_L) {
+        double u[4], v[4], X[4], Y[4], Z[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = e0 + q * NT_L;
+            const bool in = e < hi_p;
+            const int ee = in ? e : e0;
+            u[q] = p2[2 * ee]; v[q] = p2[2 * ee + 1];
+            X[q] = in ? p3[3 * ee] : 0.0; Y[q] = in ? p3[3 * ee + 1] : 0.0; Z[q] = in ? p3[3 * ee + 2] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (e0 + q * NT_L >= hi_p) continue;
+            double p[3], P[3] = {X[q], Y[q], Z[q]};
+            cvx::bearing(Ki, u[q], v[q], p);
             const double n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
             const double W[6] = {n2 - p[0] * p[0], -p[1] * p[0], n2 - p[1] * p[1],
                                  -p[2] * p[0],     -p[2] * p[1], n2 - p[2] * p[2]};
             cvx::accum_add(acc, P, W);
-        } else {
+        }
+    }
+    for (int e = max(lo, d.n_pts) + threadIdx.x; e < hi; e += NT_L) {
+        {
             const int i = e - d.n_pts;
             double a[3], c[3];
             cvx::bearing(Ki, l2[4 * i], l2[4 * i + 1], a);
