@@ -45,15 +45,14 @@ enum : int32_t {
     ST_FLAG_NOT_CERTIFIED = 0x100  // |obj - dual obj| > eps (the warning of cvxpnpl.py:516-519)
 };
 
-template <int S>
-struct Arr {
-    double* p;
-    CVX_HD double& operator[](int e) const { return p[(size_t)e * S]; }
-    // load the compiler may not merge with an earlier load of the same element
-    // (used to stop it from keeping all of V in registers across unrolled phases)
-    CVX_HD double reload(int e) const { return *(volatile const double*)(p + (size_t)e * S); }
-    CVX_HD Arr<S> sub(int off) const { return Arr<S>{p + (size_t)off * S}; }
+template <int S, class R>
+struct ArrT {
+    R* p;
+    CVX_HD R& operator[](int e) const { return p[(size_t)e * S]; }
+    CVX_HD ArrT<S, R> sub(int off) const { return ArrT<S, R>{p + (size_t)off * S}; }
 };
+template <int S>
+using Arr = ArrT<S, double>;
 
 // runtime-strided read-only / write view for global scratch
 struct GArr {
@@ -238,310 +237,38 @@ CVX_HD bool assemble(const double* K, const double* pts_2d, const double* pts_3d
     return reduce_accum(acc, Q, Bm);
 }
 
-// ---------------------------------------------------------------------------------
-// Jacobi symmetric eigensolver, register resident, compact code.
-//
-// t[55] is the packed 10x10 matrix held in REGISTERS (every index below is a
-// compile-time constant); V (eigenbasis, V[i*10+j] = component i of eigenvector
-// j) stays in the problem's strided shared-memory view.
-//
-// Pivot order: round-robin tournament, 9 rounds of 5 disjoint pairs.  To keep the
-// loop body SMALL (the instruction cache, not the FP64 pipe, bounded the fully
-// unrolled version: ncu stall_no_instruction 2.4 cycles per issue) every round
-// rotates the same fixed position pairs (0,9) (1,8) (2,7) (3,6) (4,5) and then
-// applies the fixed tournament permutation  0->0, i->i+1 (1..8), 9->1  to the
-// rows/columns of t and to the columns of V ("the players move, the tables
-// stay"), so one round body is executed nine times by a rolled loop.  The order
-// of the eigenpairs is irrelevant to the caller (lam[j] always matches column j
-// of V), and after 9 rounds the permutation is the identity again.
-//
-// The five rotations of a round commute and their angles only depend on entries
-// no other rotation of the round touches, so all five (c, s) are computed up
-// front (instruction-level parallelism across the sqrt / divide chains).
-// ---------------------------------------------------------------------------------
+// ---- type-generic strided view ---------------------------------------------------
 CVX_HD constexpr int jp_p(int k) { return k; }          // fixed pairs (k, 9-k), k = 0..4
 CVX_HD constexpr int jp_q(int k) { return 9 - k; }
 CVX_HD constexpr int jp_sigma(int i) { return i == 0 ? 0 : (i == 9 ? 1 : i + 1); }
 
-// reciprocal square root: device intrinsic path / host libm
-CVX_HD double cvx_rsqrt(double x)
-{
-#if defined(__CUDA_ARCH__)
-    return rsqrt(x);
-#else
-    return 1.0 / sqrt(x);
-#endif
-}
 
-// Rotation for pivot (p,q) annihilating a_pq (classical Jacobi, |angle| <= pi/4):
-//   d = a_qq - a_pp, b = 2 a_pq, h = sqrt(d^2 + b^2)
-//   cos^2 = (h + |d|) / (2h),  sin = sgn(d) b / (2 h cos),  tan = sin / cos
-// written with two reciprocal square roots and no division, which keeps the
-// dependent chain short (the five chains of a round are the critical path).
-CVX_HD void jacobi_cs(double app, double aqq, double apq, double& c, double& s, double& tn)
-{
-    const double d = aqq - app, b2 = 2.0 * apq;
-    const double g = fma(d, d, b2 * b2);
-    const double ad = fabs(d);
-    // negligible pivot (also covers d = b2 = 0 and underflow of g): identity rotation
-    const bool skip = !(fabs(apq) > 1e-18 * ad) || !(g > 1e-280);
-    const double ig = cvx_rsqrt(skip ? 1.0 : g);
-    const double c2 = fma(0.5 * ad, ig, 0.5);          // in [0.5, 1]
-    const double rc = cvx_rsqrt(c2);
-    const double sg = copysign(0.5, d) * b2 * ig;       // sin * cos
-    c = skip ? 1.0 : c2 * rc;
-    s = skip ? 0.0 : sg * rc;
-    tn = skip ? 0.0 : sg * rc * rc;
-}
+}  // namespace cvx
 
-// one sweep; returns the off-diagonal square sum seen at the pivots (before they
-// are annihilated)
-template <int S>
-CVX_HD double jacobi_sweep_reg(double t[55], Arr<S> V)
-{
-    double off = 0.0;
-#pragma unroll 1
-    for (int round = 0; round < 9; ++round) {
-        double cs[5], sn[5], tn[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int p = jp_p(k), q = jp_q(k);
-            const double apq = t[sidx(q, p)];
-            off = fma(apq, apq, off);
-            jacobi_cs(t[sidx(p, p)], t[sidx(q, q)], apq, cs[k], sn[k], tn[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int p = jp_p(k), q = jp_q(k);
-            const double c = cs[k], s = sn[k];
-            const double apq = t[sidx(q, p)];
-            t[sidx(p, p)] = fma(-tn[k], apq, t[sidx(p, p)]);
-            t[sidx(q, q)] = fma(tn[k], apq, t[sidx(q, q)]);
-            t[sidx(q, p)] = 0.0;
-#pragma unroll
-            for (int m = 0; m < 10; ++m) {
-                if (m == p || m == q) continue;
-                const double amp = t[sidx(m, p)], amq = t[sidx(m, q)];
-                t[sidx(m, p)] = fma(c, amp, -s * amq);
-                t[sidx(m, q)] = fma(s, amp, c * amq);
-            }
-        }
-        // tournament permutation of rows/columns of t
-        {
-            double u[55];
-#pragma unroll
-            for (int i = 0; i < 10; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) u[sidx(jp_sigma(i), jp_sigma(j))] = t[sidx(i, j)];
-#pragma unroll
-            for (int e = 0; e < 55; ++e) t[e] = u[e];
-        }
-        // rotate + permute the columns of V, two rows at a time (two independent
-        // instruction streams for the single resident warp of the scheduler)
-#pragma unroll 1
-        for (int row = 0; row < 10; row += 2) {
-            double v[2][10];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int j = 0; j < 10; ++j) v[h][j] = V[(row + h) * 10 + j];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const int p = jp_p(k), q = jp_q(k);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double vp = v[h][p], vq = v[h][q];
-                    v[h][p] = fma(cs[k], vp, -sn[k] * vq);
-                    v[h][q] = fma(sn[k], vp, cs[k] * vq);
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int j = 0; j < 10; ++j) V[(row + h) * 10 + jp_sigma(j)] = v[h][j];
-        }
-    }
-    return off;
-}
+// CVX_RELSKIP: pivots smaller than this relative to the diagonal gap are not rotated;
+// CVX_TINY: guard against d^2 + b^2 underflowing.
+#define CVX_REAL double
+#define CVX_RELSKIP 1e-18
+#define CVX_TINY 1e-280
+namespace cvx {
+#include "pnpl_dr.inl"
+}  // namespace cvx
+#undef CVX_REAL
+#undef CVX_RELSKIP
+#undef CVX_TINY
+#define CVX_REAL float
+#define CVX_RELSKIP 1e-9f
+#define CVX_TINY 1e-36f
+namespace cvx {
+namespace f32 {
+#include "pnpl_dr.inl"
+}  // namespace f32
+}  // namespace cvx
+#undef CVX_REAL
+#undef CVX_RELSKIP
+#undef CVX_TINY
 
-// T <- V' M V (packed, into the strided view T).  Rolled over blocks of two
-// columns: w_j = M v_j with M read at compile-time offsets, then one dot product
-// per (i, j) pair.  Compact code on purpose (see above).
-template <int S>
-CVX_HD void rotate_into_basis(Arr<S> M, Arr<S> V, Arr<S> T)
-{
-#pragma unroll 1
-    for (int j0 = 0; j0 < 10; j0 += 2) {
-        double w0[10], w1[10];
-        {
-            double a0[10], a1[10];
-#pragma unroll
-            for (int k = 0; k < 10; ++k) {
-                a0[k] = V[k * 10 + j0];
-                a1[k] = V[k * 10 + j0 + 1];
-                w0[k] = 0.0;
-                w1[k] = 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < 10; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) {
-                    const double m = M[sidx(r, c)];
-                    w0[r] = fma(m, a0[c], w0[r]);
-                    w1[r] = fma(m, a1[c], w1[r]);
-                    if (r != c) {
-                        w0[c] = fma(m, a0[r], w0[c]);
-                        w1[c] = fma(m, a1[r], w1[c]);
-                    }
-                }
-        }
-        // rows i = j0 .. 9 in pairs (j0 is even, so the count is even): four
-        // independent dot-product chains
-#pragma unroll 1
-        for (int i = j0; i < 10; i += 2) {
-            double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) {
-                const double va = V[k * 10 + i], vb = V[k * 10 + i + 1];
-                s00 = fma(va, w0[k], s00);
-                s01 = fma(va, w1[k], s01);
-                s10 = fma(vb, w0[k], s10);
-                s11 = fma(vb, w1[k], s11);
-            }
-            const int ba = (i * (i + 1)) / 2 + j0, bb = ((i + 1) * (i + 2)) / 2 + j0;
-            T[ba] = s00;
-            // (i, j0+1) with i == j0 is the transposed duplicate of (j0+1, j0): skip
-            if (i > j0) T[ba + 1] = s01;
-            T[bb] = s10;
-            T[bb + 1] = s11;
-        }
-    }
-}
-
-// memory-resident convenience wrapper (cold start on a matrix held in a strided
-// view); used by the extraction stage kernel only.
-template <int S>
-CVX_HD double jacobi_sweep(Arr<S> T, Arr<S> V)
-{
-    double t[55];
-#pragma unroll
-    for (int e = 0; e < 55; ++e) t[e] = T[e];
-    const double off = jacobi_sweep_reg(t, V);
-#pragma unroll
-    for (int e = 0; e < 55; ++e) T[e] = t[e];
-    return off;
-}
-
-// ---------------------------------------------------------------------------------
-// One Douglas-Rachford step of   min <Q,Z>  s.t.  Z in Affine (22 equalities of
-// cvxpnpl.py:387-448) and Z in PSD:
-//     Z  = P_psd(M)        (from the eigen-pairs lam, V of M)
-//     X  = P_aff(2 Z - M - Q/rho)
-//     M += alpha (X - Z)
-// Returns ||X - Z||_F^2, the fixed-point residual (primal residual X-Z and dual
-// residual rho (M+ - M)/alpha coincide up to scale).  Q/rho is read through `qr`
-// (45 packed entries of the 9x9 block); the eigenvalues through the strided view
-// L (10).  Also returns Z in z[] (registers) and writes the step g = alpha (X - Z)
-// (already added to M) to the strided view G for the Anderson accelerator.
-//
-// P_aff in closed form: the 15 triples are mutually orthogonal, so each is fixed by
-// subtracting its own normal component (the signed mean of its three entries when
-// sigma = 1); the remaining 7 equalities (rank 6) only touch the diagonal:
-// Z99 = 1 and the 3x3 array D[r][c] = Z[3c+r, 3c+r] has unit row and column sums.
-//
-// Homogeneous scaling (a diagonal preconditioner): the iteration runs on
-// Z' = D Z D with D = diag(1,..,1,sigma), isig = 1/sigma.  The PSD cone is invariant
-// under the congruence, Q' = Q (its last row/column is zero), Z'99 = sigma^2 and the
-// nine triples that touch row 9 pick up the coefficient 1/sigma on that entry.
-// sigma ~ 1.5 cuts the iteration count by a third on PnP/PnPL.
-//
-// rowk = 1 is the reference's SDP (22 equalities); rowk = 0 is the "rc" ablation of
-// benchmarks/toolkit/methods/rc.py:9-60 (the six row-orthonormality equalities removed).
-// ---------------------------------------------------------------------------------
-template <int S, class QR>
-CVX_HD double dr_step(Arr<S> M, Arr<S> V, Arr<S> L, Arr<S> G, QR qr, double alpha, double isig, double rowk,
-                      double z[55])
-{
-#pragma unroll
-    for (int e = 0; e < 55; ++e) z[e] = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < 10; ++j) {
-        const double lj = L[j];
-        if (lj > 0.0) {
-            double v[10];
-#pragma unroll
-            for (int k = 0; k < 10; ++k) v[k] = V[k * 10 + j];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                const double lr = lj * v[r];
-#pragma unroll
-                for (int c = 0; c <= r; ++c) z[sidx(r, c)] = fma(lr, v[c], z[sidx(r, c)]);
-            }
-        }
-    }
-    double res = 0.0;
-    const double inrm9 = 1.0 / (2.0 + isig * isig);
-#define CVX_Q(i, j) (((i) < 9 && (j) < 9) ? qr[sidx(i, j)] : 0.0)
-#define CVX_TRI(i0, j0, s0, i1, j1, s1, i2, j2, s2, ROW)                                    \
-    {                                                                                        \
-        const int e0 = sidx(i0, j0), e1 = sidx(i1, j1), e2 = sidx(i2, j2);                  \
-        const double m0 = M[e0], m1 = M[e1], m2 = M[e2];                                    \
-        const double w0 = 2.0 * z[e0] - m0 - CVX_Q(i0, j0);                                 \
-        const double w1 = 2.0 * z[e1] - m1 - CVX_Q(i1, j1);                                 \
-        const double w2 = 2.0 * z[e2] - m2 - CVX_Q(i2, j2);                                 \
-        /* third entry on the homogeneous row carries 1/sigma in the scaled problem */      \
-        const double a2 = ((i2) == 9) ? (s2) * isig : (double)(s2);                         \
-        const double r = ((s0) * w0 + (s1) * w1 + a2 * w2) *                                 \
-                         (((i2) == 9) ? inrm9 : ((ROW) ? rowk * (1.0 / 3.0) : (1.0 / 3.0)));  \
-        const double d0 = w0 - (s0) * r - z[e0];                                            \
-        const double d1 = w1 - (s1) * r - z[e1];                                            \
-        const double d2 = w2 - a2 * r - z[e2];                                              \
-        M[e0] = fma(alpha, d0, m0);                                                         \
-        M[e1] = fma(alpha, d1, m1);                                                         \
-        M[e2] = fma(alpha, d2, m2);                                                         \
-        G[e0] = alpha * d0;                                                                 \
-        G[e1] = alpha * d1;                                                                 \
-        G[e2] = alpha * d2;                                                                 \
-        res += 2.0 * (d0 * d0 + d1 * d1 + d2 * d2);                                         \
-    }
-    CVX_TRIPLES(CVX_TRI)
-#undef CVX_TRI
-    // diagonal block
-    {
-        double w[9], md[10];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            md[i] = M[sidx(i, i)];
-            w[i] = 2.0 * z[sidx(i, i)] - md[i] - qr[sidx(i, i)];
-        }
-        md[9] = M[sidx(9, 9)];
-        // D[r][c] = w[3c + r]; project onto unit row sums (over c) and column sums (over r)
-        double R[3], C[3], Gs = 0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) R[r] = w[r] + w[3 + r] + w[6 + r];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { C[c] = w[3 * c] + w[3 * c + 1] + w[3 * c + 2]; Gs += C[c]; }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int i = 3 * c + r;
-                // rowk = 0 ("rc" variant): only the column sums are constrained
-                const double x = w[i] - rowk * (R[r] - 1.0) * (1.0 / 3.0) - (C[c] - 1.0) * (1.0 / 3.0)
-                                 + rowk * (Gs - 3.0) * (1.0 / 9.0);
-                const double d = x - z[sidx(i, i)];
-                M[sidx(i, i)] = fma(alpha, d, md[i]);
-                G[sidx(i, i)] = alpha * d;
-                res = fma(d, d, res);
-            }
-        const double d9 = 1.0 / (isig * isig) - z[sidx(9, 9)];
-        M[sidx(9, 9)] = fma(alpha, d9, md[9]);
-        G[sidx(9, 9)] = alpha * d9;
-        res = fma(d9, d9, res);
-    }
-#undef CVX_Q
-    return res;
-}
+namespace cvx {
 
 // ---------------------------------------------------------------------------------
 // Anderson acceleration (type II, memory AA_M) of the DR fixed-point iteration
