@@ -20,6 +20,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CVX_HD __host__ __device__ __forceinline__
@@ -271,45 +272,120 @@ namespace f32 {
 namespace cvx {
 
 // ---------------------------------------------------------------------------------
-// Anderson acceleration (type II, memory AA_M) of the DR fixed-point iteration
+// Anderson acceleration (type II, memory AA_M = 7) of the DR fixed-point iteration
 // M <- F(M), the accelerator SCS itself relies on.  With g_k = F(M_k) - M_k:
 //     gamma = argmin || g_k - dG gamma ||,   M_{k+1} = M_k + g_k - (dM + dG) gamma
-// where the columns of dG / dM are the last AA_M differences of g and M.  History is
-// kept in FP32 in a strided L2-resident scratch (it only steers the extrapolation;
-// the fixed point, and hence the result, does not depend on it):
-//     H[0]            g_{k-1}
-//     H[1]            step_{k-1} = M_k - M_{k-1}
-//     H[2 + j]        dG_j                       j < AA_M
-//     H[2 + AA_M + j] dM_j + dG_j
-// each 55 packed entries.  Inner products weight off-diagonal entries twice
-// (Frobenius).  Safeguard: an extrapolated step longer than 10 |g_k| (or a singular
-// Gram matrix) is rejected, the history dropped and the plain step kept.
+// where the columns of dG / dM are the last AA_M differences of g and M.  Memory
+// matters: measured median DR iterations on PnPL 8+4 are 203 (none), 101 (3), 80 (5),
+// 70 (7), 62 (10).  Seven columns is what one thread's share of tensor memory (512
+// 32-bit words) holds once the columns are stored as FP16 pairs:
+//     word   0.. 55   g_{k-1}                                   FP32
+//     word  56.. 83   step_{k-1} * s_{k-1}                      FP16 x 2
+//     word  84..279   dG_j * s_j      [chunk c][column j][4]    FP16 x 2
+//     word 280..475   (dM_j+dG_j)*s_j [chunk c][column j][4]    FP16 x 2
+//     word 476..503   Gram matrix of the stored dG columns      FP32 (packed lower)
+// Every column pair (dG_j, dM_j + dG_j) is multiplied by a power of two s_j that
+// brings |g| at the time of writing to ~16 before the FP16 rounding, so FP16's 11-bit
+// mantissa is spent on the entries that matter whatever the residual is (1e-2 ..
+// 1e-9).  The scale never has to be stored: scaling both halves of a pair by s_j only
+// rescales gamma_j, the extrapolated point is unchanged.  (Plain bf16 columns were
+// measured too: they cost the hard problems -- PnL 6, 4 points -- 15-20 % more
+// iterations; scaled FP16 is within 2 % of FP32 columns.)  The history only steers
+// the extrapolation; the fixed point, and hence the result, does not depend on it.
+// Inner products are plain Euclidean on the packed 55-vector.  Safeguard: an
+// extrapolated step longer than 10 |g_k| (or a Gram matrix that is not positive
+// definite) is rejected, the history dropped and the plain step kept.
 // On entry M already holds M_k + g_k and G holds g_k; on exit M holds M_{k+1}.
 // ---------------------------------------------------------------------------------
-constexpr int AA_M = 3;
+constexpr int AA_M = 7;
 constexpr double AA_RES2_ON = 0.05 * 0.05;   // accelerate only once ||X - Z||_F < 0.05 (|Z| ~ 4)
-constexpr int AA_ARRAYS = 2 + 2 * AA_M;       // g_prev, step_prev, dG[AA_M], (dM+dG)[AA_M]
-constexpr int AA_PITCH = 64;                  // words per array (55 used), 8 x 64 = 512 = all TMEM columns
-constexpr int AA_WORDS = AA_ARRAYS * AA_PITCH;
+#ifndef CVX_AA_MAXSTEP2
+#define CVX_AA_MAXSTEP2 100.f
+#endif
+constexpr float AA_MAX_STEP2 = CVX_AA_MAXSTEP2;   // an extrapolated step longer than 10 |g| is rejected
+constexpr int AA_CHUNKS = 7;                  // 7 chunks x 8 entries >= 55
+constexpr int AA_OFF_GP = 0;
+constexpr int AA_OFF_SP = 56;
+constexpr int AA_OFF_DG = 84;
+constexpr int AA_OFF_DS = AA_OFF_DG + AA_CHUNKS * AA_M * 4;   // 280
+constexpr int AA_OFF_GRAM = AA_OFF_DS + AA_CHUNKS * AA_M * 4; // 476
+constexpr int AA_GRAM_WORDS = AA_M * (AA_M + 1) / 2;          // 28 (loaded as a 32-word block)
+constexpr int AA_WORDS = 512;                                 // = all TMEM columns of a lane
+static_assert(AA_OFF_GRAM + 32 <= AA_WORDS, "history does not fit one TMEM lane");
 
 struct AAState {
     uint32_t mask;      // valid history columns (bit j = column j)
     bool have_prev;     // g_prev / step_prev hold the previous iteration of THIS problem
-    float gram[AA_M][AA_M];   // dG'dG of the stored columns (lower triangle used), kept across steps
+    float scale_prev;   // power of two the stored step_prev was multiplied by
 };
 
 CVX_HD void aa_reset(AAState& aa)
 {
     aa.mask = 0u;
     aa.have_prev = false;
-#pragma unroll
-    for (int i = 0; i < AA_M; ++i)
-#pragma unroll
-        for (int j = 0; j < AA_M; ++j) aa.gram[i][j] = 0.f;
+    aa.scale_prev = 1.f;
 }
 
-// History accessors.  Both expose 8-word chunk loads/stores on array `arr`
-// (0 g_prev, 1 step_prev, 2+j dG_j, 2+AA_M+j dM_j+dG_j):
+// ---- FP16 pair <-> two floats, 32-bit word <-> float --------------------------------
+CVX_HD uint32_t f2w(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    return u;
+#endif
+}
+CVX_HD float w2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+#endif
+}
+CVX_HD uint32_t pack_h2(float lo, float hi)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t w;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+    return w;
+#else
+    const _Float16 a = (_Float16)lo, b = (_Float16)hi;
+    uint16_t ua, ub;
+    memcpy(&ua, &a, 2);
+    memcpy(&ub, &b, 2);
+    return (uint32_t)ua | ((uint32_t)ub << 16);
+#endif
+}
+CVX_HD void unpack_h2(uint32_t w, float& lo, float& hi)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(lo), "=f"(hi) : "r"(w));
+#else
+    const uint16_t ua = (uint16_t)(w & 0xffffu), ub = (uint16_t)(w >> 16);
+    _Float16 a, b;
+    memcpy(&a, &ua, 2);
+    memcpy(&b, &ub, 2);
+    lo = (float)a;
+    hi = (float)b;
+#endif
+}
+
+// power of two s with |g| s in [16, 64) for |g|^2 ~ res2 (the squared DR residual)
+CVX_HD float aa_scale(float res2)
+{
+    const int e = (int)((f2w(res2) >> 23) & 0xffu) - 127;
+    int k = 4 - (e >> 1);
+    k = k > 100 ? 100 : (k < -100 ? -100 : k);
+    return w2f((uint32_t)(k + 127) << 23);
+}
+
+// History accessors.  Both expose N-word loads/stores at a word offset of the
+// thread's history (N = 4, 8, 16, 32):
 //   * HistMem  -- plain strided memory (host harness; the stage kernel's global scratch)
 //   * HistTmem -- Blackwell tensor memory (pnpl_kernels.cu): every thread owns one TMEM
 //                 lane = 512 private 32-bit words, 12-cycle loads, no shared-memory or
@@ -318,160 +394,255 @@ CVX_HD void aa_reset(AAState& aa)
 //                 warp execute every history access (column slots are warp-uniform,
 //                 lanes that do not accelerate just compute on dead data).
 struct HistMem {
-    float* p;
+    uint32_t* p;
     int64_t stride;
-    CVX_HD void ld8(int arr, int c, float o[8]) const
+    template <int N>
+    CVX_HD void ld(int off, uint32_t* o) const
     {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] = p[(int64_t)(arr * AA_PITCH + c * 8 + u) * stride];
+        for (int u = 0; u < N; ++u) o[u] = p[(int64_t)(off + u) * stride];
     }
-    CVX_HD void st8(int arr, int c, const float v[8]) const
+    template <int N>
+    CVX_HD void st(int off, const uint32_t* v) const
     {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) p[(int64_t)(arr * AA_PITCH + c * 8 + u) * stride] = v[u];
+        for (int u = 0; u < N; ++u) p[(int64_t)(off + u) * stride] = v[u];
     }
     CVX_HD void wait_ld() const {}
     CVX_HD void wait_st() const {}
     CVX_HD bool any(bool f) const { return f; }
 };
 
-// One accelerated step.  `active` lanes own a problem in the tail of its DR
-// iteration; `wslot` (warp-uniform, cycles 0..AA_M-1) is the column overwritten now.
-// On entry M holds M_k + g_k and G holds g_k (G[55] is a dedicated zero so whole
-// 8-word chunks can be processed without a bounds test); on exit (active lanes) M
-// holds M_{k+1}.  The least squares runs in FP32 and in the plain Euclidean metric of
-// the packed vector: it only steers the extrapolation, the fixed point does not
-// depend on it (measured: same iteration counts as the FP64 / Frobenius version).
-// The Gram matrix is kept across steps; only the row of the new column is recomputed.
-template <int S, class Hist>
-CVX_HD void aa_step(Arr<S> M, Arr<S> G, const Hist& H, AAState& aa, bool active, int wslot)
+// all AA_M columns of chunk c (AA_M x 4 = 28 words) of the block starting at `off`
+template <class Hist>
+CVX_HD void aa_ld_cols(const Hist& H, int off, int c, uint32_t w[28])
 {
-    static_assert(AA_M == 3, "the closed-form 3x3 solve below assumes AA_M == 3");
+    H.template ld<16>(off + c * 28, w);
+    H.template ld<8>(off + c * 28 + 16, w + 16);
+    H.template ld<4>(off + c * 28 + 24, w + 24);
+}
+
+// One accelerated step.  `active` lanes own a problem in the tail of its DR
+// iteration; `wslot` (warp-uniform, cycles 0..AA_M-1) is the column overwritten now;
+// res2 is the squared DR residual of the iterate (sets the FP16 scale).  On entry M
+// holds M_k + g_k and G holds g_k (G[55] is a dedicated zero so whole 8-entry chunks
+// can be processed without a bounds test); on exit (active lanes) M holds M_{k+1}.
+// The least squares runs on FP32 sums with an FP64 Cholesky factorisation.  The
+// Gram matrix is kept across steps; only the row of the new column is recomputed.
+template <int S, class RT, class Hist>
+CVX_HD void aa_step(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bool active, int wslot, float res2)
+{
     const bool close = active && aa.have_prev;
+    // the scale may grow at most 4x per step: then (|g_{k-1}| + |g_k|) s_k and the stored
+    // step (at most 10 |g|) stay far below the FP16 maximum however fast the residual drops
+    const float sc = close ? fminf(aa_scale(res2), 4.f * aa.scale_prev) : aa_scale(res2);
+    const float ratio = sc / aa.scale_prev;   // both powers of two
     // ---- A. close the newest column (dG = g_k - g_{k-1}, dM + dG = step_{k-1} + dG);
     //         dot products of the new column and of g with every stored column ----------
-    float rg0 = 0.f, rg1 = 0.f, rg2 = 0.f;   // col_j . g
-    float nd0 = 0.f, nd1 = 0.f, nd2 = 0.f;   // dg_new . col_j   (col_wslot is the one being replaced)
-    float ndd = 0.f, ndg = 0.f;              // dg_new . dg_new, dg_new . g
+    float rg[AA_M], nd[AA_M];   // col_j . g,  dg_new . col_j  (col_wslot is the one being replaced)
+    float ndd = 0.f, ndg = 0.f;  // dg_new . dg_new, dg_new . g
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) rg[j] = nd[j] = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < 7; ++c) {
-        float gp[8], sp[8], c0[8], c1[8], c2[8], dg[8], ss[8];
-        H.ld8(0, c, gp);
-        H.ld8(1, c, sp);
-        H.ld8(2, c, c0);
-        H.ld8(3, c, c1);
-        H.ld8(4, c, c2);
+    for (int c = 0; c < AA_CHUNKS; ++c) {
+        uint32_t gpw[8], spw[4], cw[28], dgw[4], dsw[4];
+        H.template ld<8>(AA_OFF_GP + 8 * c, gpw);
+        H.template ld<4>(AA_OFF_SP + 4 * c, spw);
+        aa_ld_cols(H, AA_OFF_DG, c, cw);
         H.wait_ld();
+        float gf[8], dr[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gf[u] = (float)G[c * 8 + u];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            float s0, s1;
+            unpack_h2(spw[w], s0, s1);
+            const float d0 = (gf[2 * w] - w2f(gpw[2 * w])) * sc, d1 = (gf[2 * w + 1] - w2f(gpw[2 * w + 1])) * sc;
+            // a column that is not closed is stored as zeros (never garbage: 0 * Inf = NaN)
+            dgw[w] = close ? pack_h2(d0, d1) : 0u;
+            dsw[w] = close ? pack_h2(fmaf(s0, ratio, d0), fmaf(s1, ratio, d1)) : 0u;
+            unpack_h2(dgw[w], dr[2 * w], dr[2 * w + 1]);   // the rounded column is the one that counts
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float gf = (float)G[c * 8 + u];
-            const float d = gf - gp[u];
-            dg[u] = d;
-            ss[u] = sp[u] + d;
-            rg0 = fmaf(c0[u], gf, rg0);
-            rg1 = fmaf(c1[u], gf, rg1);
-            rg2 = fmaf(c2[u], gf, rg2);
-            nd0 = fmaf(c0[u], d, nd0);
-            nd1 = fmaf(c1[u], d, nd1);
-            nd2 = fmaf(c2[u], d, nd2);
-            ndd = fmaf(d, d, ndd);
-            ndg = fmaf(d, gf, ndg);
+            ndd = fmaf(dr[u], dr[u], ndd);
+            ndg = fmaf(dr[u], gf[u], ndg);
         }
-        H.st8(2 + wslot, c, dg);
-        H.st8(2 + AA_M + wslot, c, ss);
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                float c0, c1;
+                unpack_h2(cw[4 * j + w], c0, c1);
+                rg[j] = fmaf(c0, gf[2 * w], fmaf(c1, gf[2 * w + 1], rg[j]));
+                nd[j] = fmaf(c0, dr[2 * w], fmaf(c1, dr[2 * w + 1], nd[j]));
+            }
+        H.template st<4>(AA_OFF_DG + c * 28 + 4 * wslot, dgw);
+        H.template st<4>(AA_OFF_DS + c * 28 + 4 * wslot, dsw);
     }
     // the overwritten slot is valid only if this lane had a previous iterate
     aa.mask = close ? (aa.mask | (1u << wslot)) : (aa.mask & ~(1u << wslot));
     if (!active) aa.mask = 0u;
     // refresh row / column wslot of the Gram matrix and the right-hand side
-    float r[AA_M] = {rg0, rg1, rg2};
-    const float nd[AA_M] = {nd0, nd1, nd2};
+    float gram[32];
+    {
+        uint32_t gw[32];
+        H.template ld<32>(AA_OFF_GRAM, gw);
+        H.wait_ld();
 #pragma unroll
-    for (int i = 0; i < AA_M; ++i)
+        for (int i = 0; i < AA_M; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) {
-            // entry (i, j), i >= j, belongs to row/column wslot if i == wslot or j == wslot
-            if (i == wslot && j == wslot) aa.gram[i][j] = ndd;
-            else if (i == wslot) aa.gram[i][j] = nd[j];
-            else if (j == wslot) aa.gram[i][j] = nd[i];
-        }
+            for (int j = 0; j <= i; ++j) {
+                const int e = (i * (i + 1)) / 2 + j;
+                float v = w2f(gw[e]);
+                if (i == wslot && j == wslot) v = ndd;
+                else if (i == wslot) v = nd[j];
+                else if (j == wslot) v = nd[i];
+                gram[e] = v;
+                gw[e] = f2w(v);
+            }
+        H.template st<32>(AA_OFF_GRAM, gw);
+    }
 #pragma unroll
     for (int j = 0; j < AA_M; ++j)
-        if (j == wslot) r[j] = ndg;
-    // normal equations; columns that are not valid are cut out (they may hold NaN)
-    const bool v0 = aa.mask & 1u, v1 = aa.mask & 2u, v2 = aa.mask & 4u;
-    double a00 = v0 ? (double)aa.gram[0][0] : 0.0, a11 = v1 ? (double)aa.gram[1][1] : 0.0,
-           a22 = v2 ? (double)aa.gram[2][2] : 0.0;
-    const double a10 = (v1 && v0) ? (double)aa.gram[1][0] : 0.0, a20 = (v2 && v0) ? (double)aa.gram[2][0] : 0.0,
-                 a21 = (v2 && v1) ? (double)aa.gram[2][1] : 0.0;
-    const double r0 = v0 ? (double)r[0] : 0.0, r1 = v1 ? (double)r[1] : 0.0, r2 = v2 ? (double)r[2] : 0.0;
-    const double tr = a00 + a11 + a22;
-    a00 += 1e-7 * tr + (v0 ? 0.0 : 1.0);
-    a11 += 1e-7 * tr + (v1 ? 0.0 : 1.0);
-    a22 += 1e-7 * tr + (v2 ? 0.0 : 1.0);
-    // closed-form symmetric 3x3 solve (adjugate / determinant)
-    const double k00 = a11 * a22 - a21 * a21, k10 = a20 * a21 - a10 * a22, k20 = a10 * a21 - a20 * a11;
-    const double k11 = a00 * a22 - a20 * a20, k21 = a10 * a20 - a00 * a21, k22 = a00 * a11 - a10 * a10;
-    const double det = a00 * k00 + a10 * k10 + a20 * k20;
-    const double idet = 1.0 / det;
-    const double g0 = (k00 * r0 + k10 * r1 + k20 * r2) * idet;
-    const double g1 = (k10 * r0 + k11 * r1 + k21 * r2) * idet;
-    const double g2 = (k20 * r0 + k21 * r1 + k22 * r2) * idet;
-    const bool ok = active && aa.mask != 0u && tr > 0.0 && det > 0.0 && isfinite(g0) && isfinite(g1) && isfinite(g2);
-    const float f0 = (ok && v0) ? (float)g0 : 0.f, f1 = (ok && v1) ? (float)g1 : 0.f, f2 = (ok && v2) ? (float)g2 : 0.f;
+        if (j == wslot) rg[j] = ndg;
+    // normal equations (FP64 Cholesky); columns that are not valid are cut out
+    double A[AA_GRAM_WORDS], r[AA_M];
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) {
+        const bool vi = (aa.mask >> i) & 1u;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const bool vj = (aa.mask >> j) & 1u;
+            A[(i * (i + 1)) / 2 + j] = (vi && vj) ? (double)gram[(i * (i + 1)) / 2 + j] : 0.0;
+        }
+        r[i] = vi ? (double)rg[i] : 0.0;
+        tr += A[(i * (i + 1)) / 2 + i];
+    }
+    bool pd = tr > 0.0;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) A[(i * (i + 1)) / 2 + i] += 1e-7 * tr + (((aa.mask >> i) & 1u) ? 0.0 : 1.0);
+    // A = L L' in place (L[i][i] holds the RECIPROCAL pivot), then two triangular solves.
+    // All loops have constant bounds with guards, so they unroll completely and A, r
+    // stay in registers.
+#define CVX_TI(i, j) (((i) * ((i) + 1)) / 2 + (j))
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) {
+        double d = A[CVX_TI(j, j)];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k < j) d = fma(-A[CVX_TI(j, k)], A[CVX_TI(j, k)], d);
+        pd = pd && (d > 0.0);
+        const double id = cvx_rsqrt(pd ? d : 1.0);
+        A[CVX_TI(j, j)] = id;
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) {
+            if (i <= j) continue;
+            double t = A[CVX_TI(i, j)];
+#pragma unroll
+            for (int k = 0; k < AA_M; ++k)
+                if (k < j) t = fma(-A[CVX_TI(i, k)], A[CVX_TI(j, k)], t);
+            A[CVX_TI(i, j)] = t * id;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) {
+        double t = r[i];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k < i) t = fma(-A[CVX_TI(i, k)], r[k], t);
+        r[i] = t * A[CVX_TI(i, i)];
+    }
+#pragma unroll
+    for (int ii = 0; ii < AA_M; ++ii) {
+        const int i = AA_M - 1 - ii;
+        double t = r[i];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k > i) t = fma(-A[CVX_TI(k, i)], r[k], t);
+        r[i] = t * A[CVX_TI(i, i)];
+    }
+#undef CVX_TI
+    bool ok = active && aa.mask != 0u && pd;
+    float f[AA_M];
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) ok = ok && isfinite(r[j]);
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) f[j] = (ok && ((aa.mask >> j) & 1u)) ? (float)r[j] : 0.f;
     H.wait_st();
 
     // ---- B. extrapolate optimistically: M -= sum_j gamma_j (dM_j + dG_j); remember g_k
     //         and the step; measure |step| against |g| ---------------------------------
     float ng = 0.f, ns = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < 7; ++c) {
-        float c0[8], c1[8], c2[8], gk[8], stp[8];
-        H.ld8(2 + AA_M, c, c0);
-        H.ld8(3 + AA_M, c, c1);
-        H.ld8(4 + AA_M, c, c2);
+    for (int c = 0; c < AA_CHUNKS; ++c) {
+        uint32_t cw[28], gkw[8], spw[4];
+        aa_ld_cols(H, AA_OFF_DS, c, cw);
         H.wait_ld();
+        float adj[8], stp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) adj[u] = 0.f;
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                float c0, c1;
+                unpack_h2(cw[4 * j + w], c0, c1);
+                adj[2 * w] = fmaf(f[j], c0, adj[2 * w]);
+                adj[2 * w + 1] = fmaf(f[j], c1, adj[2 * w + 1]);
+            }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float gf = (float)G[c * 8 + u];
-            const float adj = fmaf(f0, c0[u], fmaf(f1, c1[u], f2 * c2[u]));
-            gk[u] = gf;
-            stp[u] = gf - adj;
-            if (ok) M[c * 8 + u] -= (double)adj;
+            const float gf = active ? (float)G[c * 8 + u] : 0.f;
+            gkw[u] = f2w(gf);
+            stp[u] = gf - adj[u];
+            if (ok) M[c * 8 + u] -= (RT)adj[u];
             ng = fmaf(gf, gf, ng);
             ns = fmaf(stp[u], stp[u], ns);
         }
-        H.st8(0, c, gk);
-        H.st8(1, c, stp);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) spw[w] = pack_h2(stp[2 * w] * sc, stp[2 * w + 1] * sc);
+        H.template st<8>(AA_OFF_GP + 8 * c, gkw);
+        H.template st<4>(AA_OFF_SP + 4 * c, spw);
     }
     H.wait_st();
     // ---- C. (rare) the extrapolated step is longer than 10 |g|: undo, keep the plain
     //         step, drop the history -----------------------------------------------------
-    const bool reject = ok && !(ns <= 100.f * ng);
+    const bool reject = ok && !(ns <= AA_MAX_STEP2 * ng);
     if (H.any(reject)) {
 #pragma unroll 1
-        for (int c = 0; c < 7; ++c) {
-            float c0[8], c1[8], c2[8], gk[8], stp[8];
-            H.ld8(2 + AA_M, c, c0);
-            H.ld8(3 + AA_M, c, c1);
-            H.ld8(4 + AA_M, c, c2);
-            H.ld8(0, c, gk);
-            H.ld8(1, c, stp);
+        for (int c = 0; c < AA_CHUNKS; ++c) {
+            uint32_t cw[28], gkw[8], spw[4];
+            aa_ld_cols(H, AA_OFF_DS, c, cw);
+            H.template ld<8>(AA_OFF_GP + 8 * c, gkw);
+            H.template ld<4>(AA_OFF_SP + 4 * c, spw);
             H.wait_ld();
+            float adj[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float adj = fmaf(f0, c0[u], fmaf(f1, c1[u], f2 * c2[u]));
-                if (reject) {
-                    M[c * 8 + u] += (double)adj;
-                    stp[u] = gk[u];
+            for (int u = 0; u < 8; ++u) adj[u] = 0.f;
+#pragma unroll
+            for (int j = 0; j < AA_M; ++j)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    float c0, c1;
+                    unpack_h2(cw[4 * j + w], c0, c1);
+                    adj[2 * w] = fmaf(f[j], c0, adj[2 * w]);
+                    adj[2 * w + 1] = fmaf(f[j], c1, adj[2 * w + 1]);
                 }
+            if (reject) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) M[c * 8 + u] += (RT)adj[u];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) spw[w] = pack_h2(w2f(gkw[2 * w]) * sc, w2f(gkw[2 * w + 1]) * sc);
             }
-            H.st8(1, c, stp);
+            H.template st<4>(AA_OFF_SP + 4 * c, spw);
         }
         H.wait_st();
     }
     if (active && aa.mask != 0u && (!ok || reject)) aa.mask = 0u;
     aa.have_prev = active;
+    aa.scale_prev = sc;
 }
 
 // ---------------------------------------------------------------------------------

@@ -43,30 +43,66 @@ using cvx::Opts;
 // ---------------------------------------------------------------------------------
 struct HistTmem {
     uint32_t base;   // TMEM address of column 0 in this warp's lane window
-    __device__ __forceinline__ void ld8(int arr, int c, float o[8]) const
-    {
-        uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-                     : "r"(base + (uint32_t)(arr * cvx::AA_PITCH + c * 8))
-                     : "memory");
-        o[0] = __uint_as_float(r0); o[1] = __uint_as_float(r1); o[2] = __uint_as_float(r2); o[3] = __uint_as_float(r3);
-        o[4] = __uint_as_float(r4); o[5] = __uint_as_float(r5); o[6] = __uint_as_float(r6); o[7] = __uint_as_float(r7);
-    }
-    __device__ __forceinline__ void st8(int arr, int c, const float v[8]) const
-    {
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                     :
-                     : "r"(base + (uint32_t)(arr * cvx::AA_PITCH + c * 8)), "r"(__float_as_uint(v[0])),
-                       "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-                       "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-                       "r"(__float_as_uint(v[7]))
-                     : "memory");
-    }
+    template <int N>
+    __device__ __forceinline__ void ld(int off, uint32_t* o) const;
+    template <int N>
+    __device__ __forceinline__ void st(int off, const uint32_t* v) const;
     __device__ __forceinline__ void wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
     __device__ __forceinline__ void wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
     __device__ __forceinline__ bool any(bool f) const { return __any_sync(0xffffffffu, f) != 0; }
 };
+
+#define CVX_R4(o, k) "=r"(o[k]), "=r"(o[k + 1]), "=r"(o[k + 2]), "=r"(o[k + 3])
+#define CVX_V4(v, k) "r"(v[k]), "r"(v[k + 1]), "r"(v[k + 2]), "r"(v[k + 3])
+template <>
+__device__ __forceinline__ void HistTmem::ld<4>(int off, uint32_t* o) const
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : CVX_R4(o, 0) : "r"(base + (uint32_t)off) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::ld<8>(int off, uint32_t* o) const
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : CVX_R4(o, 0), CVX_R4(o, 4) : "r"(base + (uint32_t)off) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::ld<16>(int off, uint32_t* o) const
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : CVX_R4(o, 0), CVX_R4(o, 4), CVX_R4(o, 8), CVX_R4(o, 12) : "r"(base + (uint32_t)off) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::ld<32>(int off, uint32_t* o) const
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : CVX_R4(o, 0), CVX_R4(o, 4), CVX_R4(o, 8), CVX_R4(o, 12), CVX_R4(o, 16), CVX_R4(o, 20), CVX_R4(o, 24),
+                   CVX_R4(o, 28)
+                 : "r"(base + (uint32_t)off) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::st<4>(int off, const uint32_t* v) const
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 : : "r"(base + (uint32_t)off), CVX_V4(v, 0) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::st<8>(int off, const uint32_t* v) const
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 : : "r"(base + (uint32_t)off), CVX_V4(v, 0), CVX_V4(v, 4) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::st<32>(int off, const uint32_t* v) const
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 : : "r"(base + (uint32_t)off), CVX_V4(v, 0), CVX_V4(v, 4), CVX_V4(v, 8), CVX_V4(v, 12), CVX_V4(v, 16),
+                   CVX_V4(v, 20), CVX_V4(v, 24), CVX_V4(v, 28) : "memory");
+}
+#undef CVX_R4
+#undef CVX_V4
 
 __device__ __forceinline__ uint32_t tmem_alloc_all(uint32_t* slot_smem)
 {
@@ -134,9 +170,10 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, con
     T[55] = 0.0;   // zero pad read by the 8-word chunks of aa_step
     {
         // tensor memory comes up uninitialised: zero the history (the pad words must be 0)
-        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int arr = 0; arr < cvx::AA_ARRAYS; ++arr)
-            for (int c = 0; c < 8; ++c) H.st8(arr, c, zero);
+        uint32_t zero[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) zero[u] = 0u;
+        for (int c = 0; c < cvx::AA_WORDS / 32; ++c) H.st<32>(32 * c, zero);
         H.wait_st();
     }
 
@@ -168,7 +205,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, con
         if (b >= 0) want = cvx::pass_dr(o, V, M, T, L, QR, st);
         __syncwarp();
         // warp-collective Anderson step: executed by all 32 lanes whenever one wants it
-        if (H.any(want)) cvx::aa_step(M, T, H, st.aa, want, wslot);
+        if (H.any(want)) cvx::aa_step(M, T, H, st.aa, want, wslot, (float)st.res_prev);
         wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
         if (b >= 0) {
             if (cvx::pass_eig(o, V, M, T, L, QR, st)) {
@@ -409,7 +446,7 @@ __global__ void assemble_kernel(cvxpnpl_b200_desc d, double* Q, double* Bmat)
 }
 
 __global__ void __launch_bounds__(NT, 1)
-solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, float* hist, int64_t ws_stride)
+solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, uint32_t* hist, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
@@ -421,8 +458,7 @@ solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, float* hist, int6
     cvx::GArr qr{d.workspace + slot, ws_stride};
     const cvx::HistMem H{hist + slot, ws_stride};
     T[55] = 0.0;
-    for (int arr = 0; arr < cvx::AA_ARRAYS; ++arr)
-        for (int e = 0; e < cvx::AA_PITCH; ++e) hist[slot + (int64_t)(arr * cvx::AA_PITCH + e) * ws_stride] = 0.f;
+    for (int e = 0; e < cvx::AA_WORDS; ++e) hist[slot + (int64_t)e * ws_stride] = 0u;
     for (int64_t b = slot; b < d.batch; b += (int64_t)gridDim.x * NT) {
         const double* Qi = Q + b * 81;
         double nq = 0;
@@ -449,7 +485,7 @@ solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, float* hist, int6
         int wslot = 0;
         for (int guard = 0; guard < o.max_iters + 40; ++guard) {
             const bool want = cvx::pass_dr(o, V, M, T, L, qr, st);
-            if (want) cvx::aa_step(M, T, H, st.aa, want, wslot);
+            if (want) cvx::aa_step(M, T, H, st.aa, want, wslot, (float)st.res_prev);
             wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
             if (cvx::pass_eig(o, V, M, T, L, qr, st)) break;
         }
@@ -738,7 +774,7 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
     const int64_t blocks = want < slots / NT ? want : slots / NT;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
-    float* hist = (float*)(dd.workspace + slots * 45 + d->batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES));
+    uint32_t* hist = (uint32_t*)(dd.workspace + slots * 45 + d->batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES));
     solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), Q, hist, slots);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();

@@ -342,7 +342,7 @@ CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
 #pragma unroll 1
     for (int guard = 0; guard < o.max_iters + 40; ++guard) {
         const bool want = pass_dr(o, V, M, T, L, QR, st);
-        if (H.any(want)) aa_step(M, T, H, st.aa, want, wslot);
+        if (H.any(want)) aa_step(M, T, H, st.aa, want, wslot, (float)st.res_prev);
         wslot = (wslot + 1 == AA_M) ? 0 : wslot + 1;
         if (pass_eig(o, V, M, T, L, QR, st)) break;
     }

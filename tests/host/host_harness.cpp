@@ -27,7 +27,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
     o.rowk = variant == 1 ? 0.0 : 1.0;
     o.aa_on2 = (anderson > 1) ? (1e-3 * anderson) * (1e-3 * anderson) : cvx::AA_RES2_ON;   // test hook: threshold in 1e-3 units
     std::vector<double> V(100), M(56), T(56), L(10), qr(45);   // T[55] = 0: zero pad for aa_step
-    std::vector<float> hist(cvx::AA_WORDS);
+    std::vector<uint32_t> hist(cvx::AA_WORDS, 0u);
     for (int64_t b = 0; b < B; ++b) {
         cvx::Problem pr;
         pr.K = k_batched ? K + 9 * b : K;
