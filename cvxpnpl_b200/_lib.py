@@ -32,7 +32,7 @@ class Desc(ctypes.Structure):
         ("max_iters", ctypes.c_int32),
         ("sweeps", ctypes.c_int32),
         ("variant", ctypes.c_int32),
-        ("reserved1", ctypes.c_int32),
+        ("handoff", ctypes.c_int32),
         ("rho_rel", ctypes.c_double),
         ("alpha", ctypes.c_double),
         ("sigma", ctypes.c_double),

@@ -63,11 +63,13 @@ class Workspace:
 
 def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1e-9, max_iters=2500,
                   sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, variant="full", return_Z=False, return_obj=True, workspace=None,
-                  out: Optional[BatchedPoses] = None, device=None) -> BatchedPoses:
+                  out: Optional[BatchedPoses] = None, device=None, handoff=0) -> BatchedPoses:
     """Solve B problems.  pts_2d [B,n,2], pts_3d [B,n,3], line_2d [B,m,2,2],
     line_3d [B,m,2,3], K [3,3] or [B,3,3]; any of the point / line pairs may be
     omitted (PnP / PnL / PnPL: cvxpnpl.py:523-627).  variant="rc" solves the ablation
-    of benchmarks/toolkit/methods/rc.py (row-orthonormality equalities removed)."""
+    of benchmarks/toolkit/methods/rc.py (row-orthonormality equalities removed).
+    handoff: passes after which a problem still iterating once the work queue is empty
+    moves to the warp-per-problem straggler kernel (0 = default, < 0 = never)."""
     _require_cuda()
     lib = _lib.load()
     if device is None:
@@ -151,6 +153,7 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.sigma = float(sigma)
         d.anderson = 0 if anderson else -1
         d.variant = {"full": 0, "rc": 1}[variant]
+        d.handoff = int(handoff)
         d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
         d.workspace, d.workspace_bytes = _ptr(workspace.buf), workspace.nbytes

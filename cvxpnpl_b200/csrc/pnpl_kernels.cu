@@ -16,6 +16,7 @@
 #include "pnpl_core.cuh"
 #include "pnpl_extract.cuh"
 #include "pnpl_solve.cuh"
+#include "pnpl_warp.cuh"
 
 namespace {
 
@@ -151,9 +152,18 @@ __device__ __forceinline__ cvx::Problem problem_at(const cvxpnpl_b200_desc& d, i
 // index from `counter` (lane-level work stealing), so the iteration-count spread
 // of the batch (median ~300, tail to 2500) costs no idle lanes.
 // ---------------------------------------------------------------------------------
+// control words at the head of the workspace (unsigned long long each)
+enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3 };
+
+// RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
+//   is empty, a lane whose problem is still in its DR loop `grace` passes later hands it
+//   over to the warp-per-problem kernel (pnpl_warp.cuh) through a slab entry and leaves.
+// RESUME = true: second visit for the handed-over problems, whose DR loop has been
+//   finished by straggler_kernel: polish the eigen-decomposition, park.
+template <bool RESUME>
 __global__ void __launch_bounds__(NT, 1)
-solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, const double* pre, double* park,
-                   int64_t ws_stride)
+solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const double* pre, double* park,
+                   double* slab, int grace, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
@@ -179,6 +189,8 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, con
 
     int64_t b = -1;
     bool exhausted = false;
+    int drain = 0;   // passes since this lane saw the queue empty
+    const unsigned long long n_work = RESUME ? ctrl[CTRL_NSTRAG] : (unsigned long long)d.batch;
     cvx::LaneState st;
     st.finite = false;
     st.iterating = false;
@@ -192,15 +204,30 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, con
     int wslot = 0;   // warp-uniform history column
     for (;;) {
         if (b < 0 && !exhausted) {
-            const unsigned long long nb = atomicAdd(counter, 1ULL);
-            if (nb < (unsigned long long)d.batch) {
-                b = (int64_t)nb;
-                cvx::problem_begin(pre + b * cvx::PRE_DOUBLES, o, V, M, L, QR, st);
+            const unsigned long long nb = atomicAdd(ctrl + (RESUME ? CTRL_RESUME_NEXT : CTRL_NEXT), 1ULL);
+            if (nb < n_work) {
+                if (RESUME) {
+                    b = cvx::problem_resume(slab + nb * cvx::HAND_DOUBLES, V, M, L, QR, st);
+                } else {
+                    b = (int64_t)nb;
+                    cvx::problem_begin(pre + b * cvx::PRE_DOUBLES, o, V, M, L, QR, st);
+                }
             } else {
                 exhausted = true;
             }
         }
         if (__all_sync(0xffffffffu, b < 0)) break;   // queue empty and every lane idle
+        if (!RESUME && grace >= 0 && b >= 0 && st.iterating) {
+            // hand-over: the queue is empty (nothing left to steal), this problem is still in
+            // its DR loop `grace` passes later -> the warp-per-problem kernel finishes it
+            if (drain > 0 || *(volatile unsigned long long*)(ctrl + CTRL_NEXT) >= n_work) ++drain;
+            if (drain > grace) {
+                const unsigned long long k = atomicAdd(ctrl + CTRL_NSTRAG, 1ULL);
+                cvx::problem_handoff(V, M, L, QR, st, b, slab + k * cvx::HAND_DOUBLES);
+                b = -1;
+                exhausted = true;
+            }
+        }
         bool want = false;
         if (b >= 0) want = cvx::pass_dr(o, V, M, T, L, QR, st);
         __syncwarp();
@@ -216,6 +243,58 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* counter, con
         }
     }
     tmem_free_all(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------
+// Straggler kernel: one WARP per handed-over problem (pnpl_warp.cuh).  8 warps per
+// CTA, ~9 KB of shared memory per warp.  Warps pull slab entries from a counter.
+// ---------------------------------------------------------------------------------
+constexpr int NT_W = 256;
+constexpr size_t SMEM_W_BYTES = (NT_W / 32) * sizeof(cvx::WarpSmem);
+__global__ void __launch_bounds__(NT_W) straggler_kernel(Opts o, unsigned long long* ctrl, double* slab)
+{
+    extern __shared__ double smem[];
+    cvx::WarpSmem& S = reinterpret_cast<cvx::WarpSmem*>(smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n = ctrl[CTRL_NSTRAG];
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(ctrl + CTRL_STRAG_NEXT, 1ULL);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n) break;
+        double* h = slab + k * cvx::HAND_DOUBLES;
+        // slab entry -> full-form matrices in shared memory
+        for (int e = lane; e < 100; e += 32) {
+            const int r = e / 10, c = e - 10 * r;
+            S.M[e] = h[cvx::HO_M + cvx::sidx(r, c)];
+            S.V[e] = h[cvx::HO_V + e];
+            S.Q[e] = (r < 9 && c < 9) ? h[cvx::HO_Q + cvx::sidx(r, c)] : 0.0;
+        }
+        if (lane < 10) S.L[lane] = h[cvx::HO_L + lane];
+        for (int e = lane; e < 56; e += 32) {
+            S.gp[e] = S.sp[e] = S.gk[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < cvx::AA_M; ++j) S.dG[j][e] = S.dS[j][e] = 0.f;
+        }
+        if (lane < cvx::AA_GRAM_WORDS) S.gram[lane] = 0.f;
+        if (lane < 16) S.dots[lane] = 0.f;
+        int it = (int)h[cvx::HO_IT];
+        __syncwarp();
+        bool converged = false;
+        cvx::warp_dr_loop(S, o, lane, it, converged);
+        for (int p = lane; p < 55; p += 32) {
+            int r, c;
+            cvx::unpack_idx(p, r, c);
+            h[cvx::HO_M + p] = S.M[r * 10 + c];
+        }
+        for (int e = lane; e < 100; e += 32) h[cvx::HO_V + e] = S.V[e];
+        if (lane < 10) h[cvx::HO_L + lane] = S.L[lane];
+        if (lane == 0) {
+            h[cvx::HO_IT] = (double)it;
+            h[cvx::HO_FLAGS] = converged ? 1.0 : 0.0;
+        }
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -617,11 +696,12 @@ int64_t device_slots()
 }
 
 // workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | parked results 112 x batch doubles |
-//                    pre-pass 46 x batch doubles |
+//                    pre-pass 46 x batch doubles | hand-over slab 216 x slots doubles |
 //                    AA history AA_WORDS x slots floats (stage kernel only; the fused kernel uses TMEM)]
 size_t ws_bytes_for(int64_t slots, int64_t batch)
 {
-    return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES)) *
+    return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES) +
+            (size_t)slots * cvx::HAND_DOUBLES) *
                sizeof(double) +
            (size_t)slots * cvx::AA_WORDS * sizeof(float);
 }
@@ -654,8 +734,13 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         return fail(-7, "workspace too small");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(solve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(solve_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(solve_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(straggler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W_BYTES);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_F_BYTES);
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
@@ -666,20 +751,34 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     // CTAs than there is work for
     const int64_t want = (d->batch + NT - 1) / NT;
     const int64_t blocks = want < slots / NT ? want : slots / NT;
-    // the work counter lives in front of the Q/rho scratch, the AA history behind it
-    unsigned long long* counter = (unsigned long long*)d->workspace;
+    // control words (work counters) in front of the Q/rho scratch
+    unsigned long long* ctrl = (unsigned long long*)d->workspace;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
     double* park = dd.workspace + slots * 45;
     double* pre = park + d->batch * cvx::PARK_DOUBLES;
-    cudaError_t e0 = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+    double* slab = pre + d->batch * cvx::PRE_DOUBLES;
+    // hand-over grace (passes after the queue ran dry); desc.handoff: 0 default, < 0 never
+    const int grace = d->handoff < 0 ? -1 : (d->handoff > 0 ? d->handoff : 40);
+    const Opts o = make_opts(d);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e0 = cudaMemsetAsync(ctrl, 0, WS_HEADER_DOUBLES * sizeof(double), st);
     if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
-    pre_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dd, make_opts(d), pre);
-    solve_fused_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), counter, pre,
-                                                                                  park, slots);
-    finish_kernel<<<(unsigned)((d->batch + NT_F - 1) / NT_F), NT_F, SMEM_F_BYTES, (cudaStream_t)stream>>>(
-        dd, make_opts(d), park);
+    pre_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, st>>>(dd, o, pre);
+    solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, grace, slots);
     g_launches = 3;
+    if (grace >= 0) {
+        // at most one hand-over per lane of the first kernel: blocks * NT slab entries
+        const int64_t max_strag = blocks * NT;
+        const int64_t warps_per_cta = NT_W / 32;
+        int64_t wblocks = (max_strag + warps_per_cta - 1) / warps_per_cta;
+        const int64_t wcap = (slots / NT) * 3;   // 3 CTAs of 72 KB per SM
+        if (wblocks > wcap) wblocks = wcap;
+        straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab);
+        solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, -1, slots);
+        g_launches = 5;
+    }
+    finish_kernel<<<(unsigned)((d->batch + NT_F - 1) / NT_F), NT_F, SMEM_F_BYTES, st>>>(dd, o, park);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     return 0;
@@ -774,7 +873,8 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
     const int64_t blocks = want < slots / NT ? want : slots / NT;
     cvxpnpl_b200_desc dd = *d;
     dd.workspace = d->workspace + WS_HEADER_DOUBLES;
-    uint32_t* hist = (uint32_t*)(dd.workspace + slots * 45 + d->batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES));
+    uint32_t* hist = (uint32_t*)(dd.workspace + slots * 45 + d->batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES) +
+                                  slots * cvx::HAND_DOUBLES);
     solve_sdp_kernel<<<(unsigned)blocks, NT, SMEM_BYTES, (cudaStream_t)stream>>>(dd, make_opts(d), Q, hist, slots);
     g_launches = 1;
     cudaError_t e = cudaGetLastError();

@@ -1,0 +1,435 @@
+// pnpl_warp.cuh -- warp-per-problem Douglas-Rachford iterations: the low-latency
+// path for the stragglers of a batch.
+//
+// Why it exists.  The thread-per-problem solver (pnpl_solve.cuh) is throughput
+// optimal, but one pass of one problem is a 14 k-instruction dependent stream that
+// takes ~26 us whatever else the SM does.  Iteration counts have a long tail (PnPL
+// 8+4: median 69, p99 108, max ~800 of 1e5; PnP / PnL batches contain problems that
+// run into the 2500-iteration cap), so once the work queue is empty the whole GPU
+// waits for a handful of lanes: measured, a 1e5 PnPL batch took 19.4 ms of which the
+// balanced bulk is ~11 ms, and a PnP-8 batch took 65 ms = 2500 x 26 us.
+//
+// What it does.  When the queue of the persistent kernel has run dry, every lane
+// still iterating after a grace period parks its complete DR state (M, V, lambda,
+// Q/rho, rho, iteration count: one HAND slab entry) and leaves.  This kernel then
+// gives every such problem a whole WARP: the 10x10 matrices sit in shared memory in
+// full (unpacked) form, the 32 lanes split every step by matrix entry (Z = V L+ V',
+// the affine projection: one lane per equality, T = V'MV), the Jacobi sweep applies
+// the five disjoint rotations of a round at once as 25 independent 2x2 block updates
+// (two-sided) plus 50 row updates of V, and the Anderson dot products are spread over
+// 28 lanes.  One iteration costs ~5 k cycles (~2.5 us) instead of ~26 us.  The
+// algorithm, its constants and its stopping rule are those of the thread path; only
+// the Anderson history (FP32, unscaled, in shared memory) restarts at the hand-over.
+// When the DR loop of a problem has stopped the state goes back into its slab entry
+// and the thread kernel (resume mode) polishes the eigen-decomposition and parks it
+// for finish_kernel exactly as it does for its own problems.
+#pragma once
+
+#include "pnpl_core.cuh"
+#include "pnpl_solve.cuh"
+
+namespace cvx {
+
+// ---- hand-over slab entry (doubles) ---------------------------------------------
+constexpr int HO_M = 0;        // 55 packed DR iterate
+constexpr int HO_V = 55;       // 100 eigenbasis
+constexpr int HO_L = 155;      // 10 eigenvalues
+constexpr int HO_Q = 165;      // 45 packed Q / rho
+constexpr int HO_RHO = 210;
+constexpr int HO_IT = 211;
+constexpr int HO_FLAGS = 212;  // 1 = converged
+constexpr int HO_B = 213;      // problem index
+constexpr int HAND_DOUBLES = 216;
+
+template <int S, class QRT>
+CVX_HD void problem_handoff(Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, const LaneState& st, int64_t b, double* h)
+{
+#pragma unroll 5
+    for (int e = 0; e < 55; ++e) h[HO_M + e] = M[e];
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) h[HO_V + e] = V[e];
+#pragma unroll 2
+    for (int e = 0; e < 10; ++e) h[HO_L + e] = L[e];
+#pragma unroll 5
+    for (int e = 0; e < 45; ++e) h[HO_Q + e] = QR[e];
+    h[HO_RHO] = st.rho;
+    h[HO_IT] = (double)st.it;
+    h[HO_FLAGS] = 0.0;
+    h[HO_B] = (double)b;
+}
+
+// back into the thread solver: DR loop finished, eigen-decomposition to be polished
+template <int S, class QRT>
+CVX_HD int64_t problem_resume(const double* h, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
+{
+#pragma unroll 5
+    for (int e = 0; e < 55; ++e) M[e] = h[HO_M + e];
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) V[e] = h[HO_V + e];
+#pragma unroll 2
+    for (int e = 0; e < 10; ++e) L[e] = h[HO_L + e];
+#pragma unroll 5
+    for (int e = 0; e < 45; ++e) QR[e] = h[HO_Q + e];
+    st.rho = h[HO_RHO];
+    st.it = (int32_t)h[HO_IT];
+    st.converged = h[HO_FLAGS] != 0.0;
+    st.dobj = 0.0;
+    st.phase = 1;
+    st.finite = true;
+    st.iterating = false;
+    st.res_prev = 1e300;
+    aa_reset(st.aa);
+    return (int64_t)h[HO_B];
+}
+
+#if defined(__CUDACC__)
+
+#define CVX_TRI_ROW(i0, j0, s0, i1, j1, s1, i2, j2, s2, ROW) {i0, j0, s0, i1, j1, s1, i2, j2, s2, ROW},
+__constant__ signed char c_triples[15][10] = {CVX_TRIPLES(CVX_TRI_ROW)};
+#undef CVX_TRI_ROW
+
+struct WarpSmem {
+    double M[100], V[100], T[100], X[100], Z[100], Q[100];   // full 10x10, row-major
+    double L[10], cs[10];
+    float gp[56], sp[56], gk[56];
+    float dG[AA_M][56], dS[AA_M][56];
+    float gram[AA_GRAM_WORDS], dots[16];
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ float warp_sumf(float v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// (row, column) of packed lower-triangular index p
+__device__ __forceinline__ void unpack_idx(int p, int& r, int& c)
+{
+    r = 0;
+#pragma unroll
+    for (int k = 1; k < 10; ++k) r += (p >= (k * (k + 1)) / 2) ? 1 : 0;
+    c = p - (r * (r + 1)) / 2;
+}
+
+// pivot pair k (0..4) of round r (0..8): circle method, player 9 fixed
+__device__ __forceinline__ void round_pair(int r, int k, int& p, int& q)
+{
+    int a, b;
+    if (k == 0) {
+        a = r;
+        b = 9;
+    } else {
+        a = r + k;
+        a = a >= 9 ? a - 9 : a;
+        b = r + 9 - k;
+        b = b >= 9 ? b - 9 : b;
+    }
+    p = a < b ? a : b;
+    q = a < b ? b : a;
+}
+
+// Normal equations of the Anderson step: packed Gram matrix (lower), right-hand side,
+// valid-column mask -> coefficients.  Same arithmetic as aa_step.
+__device__ __forceinline__ bool aa_solve_packed(const float* gram, const float* rg, uint32_t mask, float f[AA_M])
+{
+#define CVX_TI(i, j) (((i) * ((i) + 1)) / 2 + (j))
+    double A[AA_GRAM_WORDS], r[AA_M];
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) {
+        const bool vi = (mask >> i) & 1u;
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j)
+            if (j <= i) A[CVX_TI(i, j)] = (vi && ((mask >> j) & 1u)) ? (double)gram[CVX_TI(i, j)] : 0.0;
+        r[i] = vi ? (double)rg[i] : 0.0;
+        tr += A[CVX_TI(i, i)];
+    }
+    bool pd = tr > 0.0;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) A[CVX_TI(i, i)] += 1e-7 * tr + (((mask >> i) & 1u) ? 0.0 : 1.0);
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) {
+        double d = A[CVX_TI(j, j)];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k < j) d = fma(-A[CVX_TI(j, k)], A[CVX_TI(j, k)], d);
+        pd = pd && (d > 0.0);
+        const double id = rsqrt(pd ? d : 1.0);
+        A[CVX_TI(j, j)] = id;
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) {
+            if (i <= j) continue;
+            double t = A[CVX_TI(i, j)];
+#pragma unroll
+            for (int k = 0; k < AA_M; ++k)
+                if (k < j) t = fma(-A[CVX_TI(i, k)], A[CVX_TI(j, k)], t);
+            A[CVX_TI(i, j)] = t * id;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) {
+        double t = r[i];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k < i) t = fma(-A[CVX_TI(i, k)], r[k], t);
+        r[i] = t * A[CVX_TI(i, i)];
+    }
+#pragma unroll
+    for (int ii = 0; ii < AA_M; ++ii) {
+        const int i = AA_M - 1 - ii;
+        double t = r[i];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k > i) t = fma(-A[CVX_TI(k, i)], r[k], t);
+        r[i] = t * A[CVX_TI(i, i)];
+    }
+#undef CVX_TI
+    bool ok = mask != 0u && pd;
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) ok = ok && isfinite(r[j]);
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) f[j] = (ok && ((mask >> j) & 1u)) ? (float)r[j] : 0.f;
+    return ok;
+}
+
+// DR iterations of one problem by one warp.  S holds M, V, L, Q (= Q/rho, full form
+// with a zero last row/column); `it` continues the problem's iteration count.
+__device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, int& it, bool& converged)
+{
+    const unsigned FULL = 0xffffffffu;
+    const double isig = 1.0 / o.sigma, inrm9 = 1.0 / (2.0 + isig * isig);
+    // packed entries owned by this lane: p = lane and p = lane + 32 (< 55)
+    int er[2], ec[2];
+    unpack_idx(lane, er[0], ec[0]);
+    unpack_idx(lane + 32 < 55 ? lane + 32 : 0, er[1], ec[1]);
+    const int np = lane + 32 < 55 ? 2 : 1;
+    uint32_t mask = 0u;
+    bool have_prev = false;
+    int wslot = 0;
+    double res_prev = 1e300;
+    converged = false;
+    for (;;) {
+        // ---- 1. Z = V max(L,0) V',  W = 2 Z - M - Q/rho  (W into X) -------------------
+        _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+            const int r = er[q], c = ec[q];
+            double z = 0.0;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const double l = S.L[j];
+                if (l > 0.0) z = fma(l * S.V[r * 10 + j], S.V[c * 10 + j], z);   // warp-uniform branch
+            }
+            const double w = 2.0 * z - S.M[r * 10 + c] - S.Q[r * 10 + c];
+            S.Z[r * 10 + c] = z;
+            S.X[r * 10 + c] = w;
+            S.X[c * 10 + r] = w;
+        }
+        __syncwarp();
+        // ---- 2. X = P_aff(W): one lane per equality group (15 triples, 9 diagonal entries,
+        //         the homogeneous corner).  Inputs first, then a barrier, then the stores.
+        double x0 = 0, x1 = 0, x2 = 0;
+        int e0 = 0, e1 = 0, e2 = 0;
+        if (lane < 15) {
+            const signed char* t = c_triples[lane];
+            e0 = t[0] * 10 + t[1];
+            e1 = t[3] * 10 + t[4];
+            e2 = t[6] * 10 + t[7];
+            const double s0 = t[2], s1 = t[5];
+            const double a2 = (t[6] == 9) ? t[8] * isig : (double)t[8];
+            const double w0 = S.X[e0], w1 = S.X[e1], w2 = S.X[e2];
+            const double k = (t[6] == 9) ? inrm9 : (t[9] ? o.rowk * (1.0 / 3.0) : (1.0 / 3.0));
+            const double rr = (s0 * w0 + s1 * w1 + a2 * w2) * k;
+            x0 = w0 - s0 * rr;
+            x1 = w1 - s1 * rr;
+            x2 = w2 - a2 * rr;
+        } else if (lane >= 16 && lane < 25) {
+            const int i = lane - 16, cc = i / 3, rr = i % 3;
+            double R = 0, C = 0, G = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double wk = S.X[k * 11];
+                G += wk;
+                if (k % 3 == rr) R += wk;
+                if (k / 3 == cc) C += wk;
+            }
+            x0 = S.X[i * 11] - o.rowk * (R - 1.0) * (1.0 / 3.0) - (C - 1.0) * (1.0 / 3.0) + o.rowk * (G - 3.0) * (1.0 / 9.0);
+            e0 = i * 11;
+        }
+        __syncwarp();
+        if (lane < 15) {
+            S.X[e0] = x0;
+            S.X[e1] = x1;
+            S.X[e2] = x2;
+        } else if (lane >= 16 && lane < 25) {
+            S.X[e0] = x0;
+        } else if (lane == 25) {
+            S.X[99] = o.sigma * o.sigma;
+        }
+        __syncwarp();
+        // ---- 3. M += alpha (X - Z); the step g = alpha (X - Z) replaces Z; residual -----
+        double rs = 0.0;
+        _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+            const int r = er[q], c = ec[q];
+            const double d = S.X[r * 10 + c] - S.Z[r * 10 + c];
+            const double m = fma(o.alpha, d, S.M[r * 10 + c]);
+            S.M[r * 10 + c] = m;
+            S.M[c * 10 + r] = m;
+            S.Z[r * 10 + c] = o.alpha * d;
+            rs = fma((r == c) ? 1.0 : 2.0, d * d, rs);
+        }
+        const double res = warp_sum(rs);
+        ++it;
+        if (!(res > o.eps2)) {   // also leaves on NaN
+            converged = (res <= o.eps2);
+            break;
+        }
+        if (it >= o.max_iters) break;
+        __syncwarp();
+        // ---- 4. Anderson acceleration in the tail (same rules as pass_dr / aa_step) ------
+        if (o.anderson) {
+            const bool tail = res < o.aa_on2;
+            if (!tail || res > 4.0 * res_prev) {
+                mask = 0u;
+                have_prev = false;
+            }
+            res_prev = res;
+            if (tail) {
+                const bool close = have_prev;
+                _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+                    const int p = lane + 32 * q;
+                    const float gf = (float)S.Z[er[q] * 10 + ec[q]];
+                    const float d = gf - S.gp[p];
+                    S.dG[wslot][p] = close ? d : 0.f;
+                    S.dS[wslot][p] = close ? S.sp[p] + d : 0.f;
+                    S.gk[p] = gf;
+                }
+                mask = close ? (mask | (1u << wslot)) : (mask & ~(1u << wslot));
+                __syncwarp();
+                // 14 dot products (col_j . g, col_j . col_wslot), each split over two lanes
+                {
+                    const int k = lane >> 1, h = lane & 1;
+                    float acc = 0.f;
+                    if (k < 2 * AA_M) {
+                        const float* a = S.dG[k < AA_M ? k : k - AA_M];
+                        const float* bv = (k < AA_M) ? S.gk : S.dG[wslot];
+                        const int lo = h * 28, hi = h ? 55 : 28;
+                        for (int p = lo; p < hi; ++p) acc = fmaf(a[p], bv[p], acc);
+                    }
+                    acc += __shfl_xor_sync(FULL, acc, 1);
+                    if (k < 2 * AA_M && h == 0) S.dots[k] = acc;
+                }
+                __syncwarp();
+                if (lane < AA_M) {
+                    const int i = lane > wslot ? lane : wslot, j = lane > wslot ? wslot : lane;
+                    S.gram[(i * (i + 1)) / 2 + j] = S.dots[AA_M + lane];
+                }
+                __syncwarp();
+                float gr[AA_GRAM_WORDS], rg[AA_M], f[AA_M];
+#pragma unroll
+                for (int e = 0; e < AA_GRAM_WORDS; ++e) gr[e] = S.gram[e];
+#pragma unroll
+                for (int j = 0; j < AA_M; ++j) rg[j] = S.dots[j];
+                const bool ok = aa_solve_packed(gr, rg, mask, f);
+                float adj[2] = {0.f, 0.f}, ng = 0.f, ns = 0.f;
+                _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+                    const int p = lane + 32 * q;
+#pragma unroll
+                    for (int j = 0; j < AA_M; ++j) adj[q] = fmaf(f[j], S.dS[j][p], adj[q]);
+                    const float gf = S.gk[p], stp = gf - adj[q];
+                    ng = fmaf(gf, gf, ng);
+                    ns = fmaf(stp, stp, ns);
+                }
+                ng = warp_sumf(ng);
+                ns = warp_sumf(ns);
+                const bool apply = ok && (ns <= AA_MAX_STEP2 * ng);
+                _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+                    const int p = lane + 32 * q, r = er[q], c = ec[q];
+                    const float gf = S.gk[p];
+                    if (apply) {
+                        const double m = S.M[r * 10 + c] - (double)adj[q];
+                        S.M[r * 10 + c] = m;
+                        S.M[c * 10 + r] = m;
+                    }
+                    S.gp[p] = gf;
+                    S.sp[p] = apply ? gf - adj[q] : gf;
+                }
+                if (mask != 0u && !apply) mask = 0u;
+                have_prev = true;
+                __syncwarp();
+            }
+        }
+        wslot = (wslot + 1 == AA_M) ? 0 : wslot + 1;
+        // ---- 5. T = V' M V  (M V into X, then the lower triangle of V' (M V), mirrored) ---
+        for (int e = lane; e < 100; e += 32) {
+            const int r = e / 10, c = e - 10 * r;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) s = fma(S.M[r * 10 + k], S.V[k * 10 + c], s);
+            S.X[e] = s;
+        }
+        __syncwarp();
+        _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+            const int r = er[q], c = ec[q];
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) s = fma(S.V[k * 10 + r], S.X[k * 10 + c], s);
+            S.T[r * 10 + c] = s;
+            S.T[c * 10 + r] = s;
+        }
+        __syncwarp();
+        // ---- 6. one Jacobi sweep: 9 rounds of 5 disjoint rotations.  Round: lanes 0..4
+        //         compute (c, s); then 25 lanes update one 2x2 block of T each
+        //         (T' = J'TJ, blocks are disjoint -> in place) and all lanes rotate rows of V.
+#pragma unroll 1
+        for (int round = 0; round < 9; ++round) {
+            if (lane < 5) {
+                int p, q;
+                round_pair(round, lane, p, q);
+                double c, s, tn;
+                jacobi_cs(S.T[p * 10 + p], S.T[q * 10 + q], S.T[q * 10 + p], c, s, tn);
+                S.cs[2 * lane] = c;
+                S.cs[2 * lane + 1] = s;
+            }
+            __syncwarp();
+            if (lane < 25) {
+                const int ka = lane / 5, kb = lane - 5 * ka;
+                int pa, qa, pb, qb;
+                round_pair(round, ka, pa, qa);
+                round_pair(round, kb, pb, qb);
+                const double ca = S.cs[2 * ka], sa = S.cs[2 * ka + 1], cb = S.cs[2 * kb], sb = S.cs[2 * kb + 1];
+                const double b00 = S.T[pa * 10 + pb], b01 = S.T[pa * 10 + qb], b10 = S.T[qa * 10 + pb],
+                             b11 = S.T[qa * 10 + qb];
+                const double y00 = ca * b00 - sa * b10, y01 = ca * b01 - sa * b11;
+                const double y10 = sa * b00 + ca * b10, y11 = sa * b01 + ca * b11;
+                const bool dg = ka == kb;   // the pivot itself is annihilated exactly
+                S.T[pa * 10 + pb] = y00 * cb - y01 * sb;
+                S.T[pa * 10 + qb] = dg ? 0.0 : y00 * sb + y01 * cb;
+                S.T[qa * 10 + pb] = dg ? 0.0 : y10 * cb - y11 * sb;
+                S.T[qa * 10 + qb] = y10 * sb + y11 * cb;
+            }
+            for (int v = lane; v < 50; v += 32) {
+                const int i = v / 5, k = v - 5 * i;
+                int p, q;
+                round_pair(round, k, p, q);
+                const double c = S.cs[2 * k], s = S.cs[2 * k + 1];
+                const double vp = S.V[i * 10 + p], vq = S.V[i * 10 + q];
+                S.V[i * 10 + p] = fma(c, vp, -s * vq);
+                S.V[i * 10 + q] = fma(s, vp, c * vq);
+            }
+            __syncwarp();
+        }
+        if (lane < 10) S.L[lane] = S.T[lane * 11];
+        __syncwarp();
+    }
+    __syncwarp();
+}
+
+#endif  // __CUDACC__
+
+}  // namespace cvx

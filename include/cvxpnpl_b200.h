@@ -64,7 +64,9 @@ typedef struct cvxpnpl_b200_desc {
     int32_t sweeps;         /* Jacobi sweeps per ADMM iteration (warm started); 0 = default */
     int32_t variant;        /* 0: the reference's SDP (cvxpnpl.py:387-448); 1: "rc" ablation with the six
                                row-orthonormality equalities removed (benchmarks/toolkit/methods/rc.py:9-60) */
-    int32_t reserved1;
+    int32_t handoff;        /* stragglers: once the work queue of the persistent kernel is empty, a problem still
+                               iterating this many passes later is finished by the warp-per-problem kernel.
+                               0 = default (40), < 0 = never hand over */
     double rho_rel;         /* ADMM penalty = rho_rel * ||Q||_F ; 0 = default */
     double alpha;           /* over-relaxation in (0,2); 0 = default */
     double sigma;           /* homogeneous-coordinate scaling (preconditioner); 0 = default */

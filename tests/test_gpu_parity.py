@@ -393,3 +393,30 @@ def test_large_n_assembly(cb):
     assert ang.max() < 2e-3 and terr.max() < 2e-3      # 2000 points average the 1 px noise down
     poses = cb.pnp(d["pts_2d"][0], d["pts_3d"][0], d["K"])
     assert len(poses) == 1 and synth.rotation_angle(poses[0][0], res.R[0, 0].cpu().numpy()) < 1e-9
+
+
+@pytest.mark.parametrize("n_pts,n_lines", [(8, 4), (0, 6), (4, 0)])
+def test_straggler_warp_path_matches_thread_path(cb, n_pts, n_lines):
+    """The warp-per-problem straggler kernel (csrc/pnpl_warp.cuh) runs the same DR
+    iteration as the thread-per-problem solver.  handoff=1 pushes every problem
+    through it after one pass (the batch is smaller than the grid, so the queue is
+    empty at once); handoff=-1 never hands over.  Same poses, same statuses."""
+    from cvxpnpl_b200 import synth
+    B = 2000
+    d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=77)
+    a = _solve(cb, d, n_pts, n_lines, handoff=-1)
+    w = _solve(cb, d, n_pts, n_lines, handoff=1)
+    assert a.launches == 3 and w.launches == 5
+    sa, sw = (a.status & 0xFF).cpu().numpy(), (w.status & 0xFF).cpu().numpy()
+    ok = (sa == 0) & (sw == 0) & (a.n_poses.cpu().numpy() == 1) & (w.n_poses.cpu().numpy() == 1)
+    assert ok.mean() > (0.95 if n_pts + n_lines > 4 else 0.5)
+    # a problem converges on both paths or on neither, up to the few that sit at the cap
+    assert (sa != sw).mean() < (0.02 if n_pts + n_lines > 4 else 0.06)
+    Ra, Rw = a.R[:, 0].cpu().numpy()[ok], w.R[:, 0].cpu().numpy()[ok]
+    ta, tw = a.t[:, 0].cpu().numpy()[ok], w.t[:, 0].cpu().numpy()[ok]
+    ang = synth.rotation_angle(Ra, Rw)
+    terr = np.linalg.norm(ta - tw, axis=1) / np.linalg.norm(ta, axis=1)
+    assert ang.max() <= ROT_TOL and terr.max() <= T_TOL, (ang.max(), terr.max())
+    ia, iw = a.iters.cpu().numpy()[ok], w.iters.cpu().numpy()[ok]
+    # the hand-over only restarts the Anderson history: similar iteration counts
+    assert np.median(iw) <= 1.3 * np.median(ia) + 10
