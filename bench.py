@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--noise", type=float, default=1.0, help="pixel noise sigma (synth.py grid: 0,1,2)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--admm", default="f64", choices=["f64", "f32"],
+                    help="f64: FP64 ADMM throughout (the headline, BASELINE.json configs[2]); f32: FP32 first "
+                         "phase + FP64 tail and extraction (configs[3]), a side measurement")
     ap.add_argument("--large-n", type=int, default=0,
                     help="side measurement (not the headline): HBM roofline of the streaming assembly with this "
                          "many points per problem (benchmarks/scalability/pnp.py regime)")
@@ -220,7 +223,8 @@ def run_ours(a):
         nonlocal out
         out = cb.solve_batched(K, pts_2d=inp["pts_2d"] if n_pts else None, pts_3d=inp["pts_3d"] if n_pts else None,
                                line_2d=inp["line_2d"] if n_lines else None,
-                               line_3d=inp["line_3d"] if n_lines else None, workspace=ws, out=out)
+                               line_3d=inp["line_3d"] if n_lines else None, workspace=ws, out=out,
+                               admm_dtype=a.admm)
         return out
 
     def pack(o):
@@ -274,19 +278,40 @@ def run_ours(a):
     ms_dev = timed(step_device, a.steps, a.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    # kernel-only time for the roofline: CUDA events around the solve call alone
-    # (torch's current stream is the stream the kernel is launched on)
-    kev = []
+    # kernel-only times for the roofline: CUDA events recorded by the library between its
+    # launches, on the stream they are launched on (torch's current stream), over a
+    # second pass of `steps` L2-flushed steps
+    ksum, ms_kernel = {}, 0.0
     for _ in range(a.steps):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        kernel_step(devin)
+        out = cb.solve_batched(K, pts_2d=devin["pts_2d"] if n_pts else None, pts_3d=devin["pts_3d"] if n_pts else None,
+                               line_2d=devin["line_2d"] if n_lines else None,
+                               line_3d=devin["line_3d"] if n_lines else None, workspace=ws, out=out,
+                               admm_dtype=a.admm, timing=True)
         e.record()
-        kev.append((s, e))
-    torch.cuda.synchronize()
-    ms_kernel = sum(s.elapsed_time(e) for s, e in kev) / a.steps
+        for k, v in cb.last_kernel_times().items():
+            ksum[k] = ksum.get(k, 0.0) + v
+        ms_kernel += s.elapsed_time(e)
+    ms_kernel /= a.steps
+    kernel_ms = {k: v / a.steps for k, v in ksum.items() if v > 0}
+    dominant = max(kernel_ms, key=kernel_ms.get)
     launches_per_step = out.launches
+
+    # side measurement (not the headline): "fp32 ADMM + fp64 extraction" (BASELINE.json
+    # configs[3] precision mode) on the same batch, device-resident inputs
+    ms_mixed = None
+    if a.admm == "f64":
+        def step_mixed():
+            nonlocal out
+            out = cb.solve_batched(K, pts_2d=devin["pts_2d"] if n_pts else None,
+                                   pts_3d=devin["pts_3d"] if n_pts else None,
+                                   line_2d=devin["line_2d"] if n_lines else None,
+                                   line_3d=devin["line_3d"] if n_lines else None, workspace=ws, out=out,
+                                   admm_dtype="f32")
+        ms_mixed = timed(step_mixed, a.steps, a.warmup)
+        kernel_step(devin)   # leave the FP64 result in `out` for the quality block
 
     ms_e2e = timed(step_e2e, a.steps, a.warmup)
 
@@ -308,11 +333,12 @@ def run_ours(a):
         value = total / (ms_dev * 1e-3)
         e2e = total / (ms_e2e * 1e-3)
         bpp = BYTES_PER_PROBLEM.get((n_pts, n_lines), 8 * (5 * n_pts + 10 * n_lines) + 96)
-        achieved = bpp * B / (ms_kernel * 1e-3) / 1e9
+        achieved = bpp * B / (kernel_ms[dominant] * 1e-3) / 1e9
+        flops = kc.get("fp64_flops_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64" if a.admm == "f64" else "f32 first phase + f64 tail/extraction", "data": "synthetic",
             "config": {"workload": f"{B} x PnPL ({n_pts} pts + {n_lines} lines) per GPU, fp64, sigma={a.noise}px, "
                                    f"Kinect K (BASELINE.json configs[2])",
                        "problems_per_gpu_per_step": B, "eps": 1e-9, "max_iters": 2500,
@@ -326,19 +352,21 @@ def run_ours(a):
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": (kc["dram_bytes_read"] + kc["dram_bytes_write"]) if kc else None,
                          "peak_kind": peak_kind,
-                         "kernel": "solve_fused_kernel (+ pre_kernel, finish_kernel: 1.7 % of the step)",
-                         "kernel_ms": ms_kernel,
+                         "kernel": dominant, "kernel_ms": kernel_ms[dominant],
+                         "all_kernels_ms": kernel_ms, "step_ms": ms_kernel,
                          "algorithmic_bytes_per_problem": bpp,
                          "note": "the path is compute/latency bound in shared memory + fp64 pipe, not HBM bound "
                                  "(SURVEY.md 8d): the HBM fraction is reported as asked, see DESIGN.md"},
             # what actually bounds the kernel: the FP64 pipe + shared memory, fed by one warp
-            # per scheduler.  flops per pass counted from the ncu instruction mix (profiles/)
-            "fp64": {"peak_tflops_measured": fp64_peak,
-                     "flops_per_problem_pass": kc.get("fp64_flops_per_problem_pass"),
-                     "achieved_tflops": (kc["fp64_flops_per_problem_pass"] * float(iters.mean() + 2) * B
-                                         / (ms_kernel * 1e-3) / 1e12) if kc else None,
-                     "frac": (kc["fp64_flops_per_problem_pass"] * float(iters.mean() + 2) * B
-                              / (ms_kernel * 1e-3) / 1e12 / fp64_peak) if kc else None},
+            # per scheduler.  FP64 flops of the dominant kernel per launch counted by ncu
+            # (profiles/r1_kernel_constants.json), over its measured duration here
+            "fp64": {"peak_tflops_measured": fp64_peak, "flops_per_launch": flops,
+                     "achieved_tflops": (flops / (kernel_ms[dominant] * 1e-3) / 1e12) if flops else None,
+                     "frac": (flops / (kernel_ms[dominant] * 1e-3) / 1e12 / fp64_peak) if flops else None},
+            "mixed_precision_side": ({"what": "fp32 ADMM first phase + fp64 tail and extraction (configs[3] mode) on "
+                                              "the same batch; not the headline",
+                                      "value": total / (ms_mixed * 1e-3), "unit": UNIT,
+                                      "ms_per_step": ms_mixed / a.steps} if ms_mixed else None),
             "quality": {"status_hist": np.bincount(st, minlength=5).tolist(),
                         "iters_median": float(np.median(iters)), "iters_p99": float(np.percentile(iters, 99)),
                         "iters_max": int(iters.max()), "rot_err_vs_gt_median_rad": float(np.nanmedian(ang)),

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvxpnpl_b200.so")
+# CVXPNPL_B200_LIB: developer override (A/B builds of the same C ABI)
+LIB_PATH = os.environ.get("CVXPNPL_B200_LIB") or os.path.join(_HERE, "libcvxpnpl_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
@@ -45,6 +46,8 @@ class Desc(ctypes.Structure):
         ("Z", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", ctypes.c_size_t),
+        ("fp32_iters", ctypes.c_int32),
+        ("timing", ctypes.c_int32),
     ]
 
 
@@ -59,6 +62,7 @@ EXPORTS = (
     "cvxpnpl_b200_last_launch_count",
     "cvxpnpl_b200_fp64_probe",
     "cvxpnpl_b200_null",
+    "cvxpnpl_b200_kernel_times",
 )
 
 _lib = None
@@ -94,6 +98,8 @@ def load():
                                          ctypes.c_void_p, ctypes.c_void_p]
     lib.cvxpnpl_b200_null.restype = ctypes.c_int
     lib.cvxpnpl_b200_null.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p]
+    lib.cvxpnpl_b200_kernel_times.restype = ctypes.c_int
+    lib.cvxpnpl_b200_kernel_times.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.cvxpnpl_b200_last_launch_count.restype = ctypes.c_int
     lib.cvxpnpl_b200_fp64_probe.restype = ctypes.c_int
     lib.cvxpnpl_b200_fp64_probe.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,

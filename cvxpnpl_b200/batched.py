@@ -63,13 +63,17 @@ class Workspace:
 
 def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1e-9, max_iters=2500,
                   sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, variant="full", return_Z=False, return_obj=True, workspace=None,
-                  out: Optional[BatchedPoses] = None, device=None, handoff=0) -> BatchedPoses:
+                  out: Optional[BatchedPoses] = None, device=None, handoff=0, admm_dtype="f64",
+                  fp32_iters=400, timing=False) -> BatchedPoses:
     """Solve B problems.  pts_2d [B,n,2], pts_3d [B,n,3], line_2d [B,m,2,2],
     line_3d [B,m,2,3], K [3,3] or [B,3,3]; any of the point / line pairs may be
     omitted (PnP / PnL / PnPL: cvxpnpl.py:523-627).  variant="rc" solves the ablation
     of benchmarks/toolkit/methods/rc.py (row-orthonormality equalities removed).
     handoff: passes after which a problem still iterating once the work queue is empty
-    moves to the warp-per-problem straggler kernel (0 = default, < 0 = never)."""
+    moves to the warp-per-problem straggler kernel (0 = default, < 0 = never).
+    admm_dtype="f32": "fp32 ADMM + fp64 extraction" (BASELINE.json configs[3]) -- the
+    iterations that bring a problem into the linear tail run in FP32 (at most
+    fp32_iters), the FP64 solver finishes to `eps`."""
     _require_cuda()
     lib = _lib.load()
     if device is None:
@@ -154,6 +158,8 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.anderson = 0 if anderson else -1
         d.variant = {"full": 0, "rc": 1}[variant]
         d.handoff = int(handoff)
+        d.fp32_iters = int(fp32_iters) if admm_dtype == "f32" else 0
+        d.timing = int(bool(timing))
         d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
         d.workspace, d.workspace_bytes = _ptr(workspace.buf), workspace.nbytes
@@ -303,3 +309,16 @@ def measure_fp64_peak(device=None, iters=4000, repeats=5):
             torch.cuda.synchronize(device)
             best = min(best, s.elapsed_time(e))
     return flops.value / (best * 1e-3) / 1e12
+
+
+KERNEL_NAMES = ("pre_kernel", "admm32_kernel", "ortho_kernel", "solve_fused_kernel", "straggler_kernel",
+                "solve_fused_kernel<resume>", "finish_kernel")
+
+
+def last_kernel_times():
+    """Device time (ms) of each kernel of the last `solve_batched(..., timing=True)` on this
+    host thread (CUDA events on the launching stream, recorded by the library)."""
+    lib = _lib.load()
+    ms = (ctypes.c_float * len(KERNEL_NAMES))()
+    _lib.check(lib.cvxpnpl_b200_kernel_times(ms, len(KERNEL_NAMES)))
+    return dict(zip(KERNEL_NAMES, [float(x) for x in ms]))

@@ -62,6 +62,13 @@ struct GArr {
     CVX_HD double& operator[](int e) const { return p[(int64_t)e * stride]; }
 };
 
+template <class R>
+struct GArrT {
+    R* p;
+    int64_t stride;
+    CVX_HD R& operator[](int e) const { return p[(int64_t)e * stride]; }
+};
+
 // packed lower-triangular (row-major) index of a symmetric matrix
 CVX_HD int sidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j + 1)) / 2 + i; }
 

@@ -27,6 +27,27 @@ constexpr size_t SMEM_BYTES = (size_t)NT * SMEM_DOUBLES * sizeof(double);
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 
+// optional per-kernel timing of the last `solve` (desc.timing != 0): CUDA events on the
+// caller's stream between the launches.  Slots: pre, admm32, ortho, fused, straggler,
+// resume, finish.
+constexpr int N_TIMED = 7;
+thread_local cudaEvent_t g_ev[N_TIMED + 1];
+thread_local bool g_ev_ready = false;
+thread_local int g_ev_slot[N_TIMED + 1];   // kernel slot that starts at event i, -1 = end
+thread_local int g_ev_n = 0;
+
+void mark(bool on, int slot, cudaStream_t st)
+{
+    if (!on || g_ev_n > N_TIMED) return;
+    if (!g_ev_ready) {
+        for (int i = 0; i <= N_TIMED; ++i) cudaEventCreate(&g_ev[i]);
+        g_ev_ready = true;
+    }
+    g_ev_slot[g_ev_n] = slot;
+    cudaEventRecord(g_ev[g_ev_n], st);
+    ++g_ev_n;
+}
+
 int fail(int code, const char* msg)
 {
     snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -153,7 +174,7 @@ __device__ __forceinline__ cvx::Problem problem_at(const cvxpnpl_b200_desc& d, i
 // of the batch (median ~300, tail to 2500) costs no idle lanes.
 // ---------------------------------------------------------------------------------
 // control words at the head of the workspace (unsigned long long each)
-enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3 };
+enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3, CTRL_NEXT32 = 4 };
 
 // RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
 //   is empty, a lane whose problem is still in its DR loop `grace` passes later hands it
@@ -163,7 +184,7 @@ enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3
 template <bool RESUME>
 __global__ void __launch_bounds__(NT, 1)
 solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const double* pre, double* park,
-                   double* slab, int grace, int64_t ws_stride)
+                   double* slab, const double* warm, int grace, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
@@ -210,7 +231,11 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
                     b = cvx::problem_resume(slab + nb * cvx::HAND_DOUBLES, V, M, L, QR, st);
                 } else {
                     b = (int64_t)nb;
-                    cvx::problem_begin(pre + b * cvx::PRE_DOUBLES, o, V, M, L, QR, st);
+                    if (warm)   // the FP32 first phase has already brought the problem into the tail
+                        cvx::problem_begin_warm(pre + b * cvx::PRE_DOUBLES, warm + b * cvx::WARM_DOUBLES, o, V, M, L, QR,
+                                                st);
+                    else
+                        cvx::problem_begin(pre + b * cvx::PRE_DOUBLES, o, V, M, L, QR, st);
                 }
             } else {
                 exhausted = true;
@@ -246,12 +271,77 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
 }
 
 // ---------------------------------------------------------------------------------
+// FP32 first phase (desc.fp32_iters > 0; BASELINE.json configs[3]).  Same persistent,
+// work-stealing structure as the FP64 solver, but the per-problem state is 221 floats:
+// 256 problems per CTA, two warps per scheduler.  A problem leaves when its DR residual
+// is below the threshold from which the FP64 solver accelerates (||X - Z||_F < 0.05),
+// or at the FP32 iteration cap.  No Anderson steps, no tensor memory.
+// ---------------------------------------------------------------------------------
+constexpr int NT32 = 256;
+constexpr size_t SMEM32_BYTES = (size_t)NT32 * SMEM_DOUBLES * sizeof(float);
+__global__ void __launch_bounds__(NT32, 1)
+admm32_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const double* pre, double* warm, float* qr32,
+              int64_t stride32, int cap32)
+{
+    extern __shared__ float smf[];
+    const int tid = threadIdx.x;
+    const int64_t slot = (int64_t)blockIdx.x * NT32 + tid;
+    cvx::ArrT<NT32, float> V{smf + tid};
+    cvx::ArrT<NT32, float> M{smf + (size_t)100 * NT32 + tid};
+    cvx::ArrT<NT32, float> T{smf + (size_t)155 * NT32 + tid};
+    cvx::ArrT<NT32, float> L{smf + (size_t)211 * NT32 + tid};
+    cvx::GArrT<float> QR{qr32 + slot, stride32};
+    const float thr2 = (float)o.aa_on2;
+    int64_t b = -1;
+    bool exhausted = false, finite = false;
+    int it = 0;
+    for (;;) {
+        if (b < 0 && !exhausted) {
+            const unsigned long long nb = atomicAdd(ctrl + CTRL_NEXT32, 1ULL);
+            if (nb < (unsigned long long)d.batch) {
+                b = (int64_t)nb;
+                const double* pb = pre + b * cvx::PRE_DOUBLES;
+                cvx::problem_begin32(pb, o, V, M, L, QR);
+                finite = isfinite(pb[45]);
+                it = 0;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, b < 0)) break;
+        if (b >= 0) {
+            bool done = true;
+            if (finite) {
+                const float res = cvx::pass32(o, V, M, T, L, QR);
+                ++it;
+                done = !(res > thr2) || it >= cap32;   // a NaN residual leaves as well
+                // queue empty: nothing left to steal, so do not wait for the slow ones here --
+                // any M is a valid DR state, the FP64 solver takes over where this one stops
+                done = done || *(volatile unsigned long long*)(ctrl + CTRL_NEXT32) >= (unsigned long long)d.batch;
+            }
+            if (done) {
+                cvx::problem_export32(V, M, L, it, warm + b * cvx::WARM_DOUBLES);
+                b = -1;
+            }
+        }
+    }
+}
+
+// exported FP32 eigenbases -> orthonormal in FP64 (lane-parallel, one thread per problem)
+__global__ void __launch_bounds__(128) ortho_kernel(int64_t batch, double* warm)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    cvx::warm_orthonormalise(warm + b * cvx::WARM_DOUBLES);
+}
+
+// ---------------------------------------------------------------------------------
 // Straggler kernel: one WARP per handed-over problem (pnpl_warp.cuh).  8 warps per
 // CTA, ~9 KB of shared memory per warp.  Warps pull slab entries from a counter.
 // ---------------------------------------------------------------------------------
 constexpr int NT_W = 256;
 constexpr size_t SMEM_W_BYTES = (NT_W / 32) * sizeof(cvx::WarpSmem);
-__global__ void __launch_bounds__(NT_W) straggler_kernel(Opts o, unsigned long long* ctrl, double* slab)
+__global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned long long* ctrl, double* slab)
 {
     extern __shared__ double smem[];
     cvx::WarpSmem& S = reinterpret_cast<cvx::WarpSmem*>(smem)[threadIdx.x >> 5];
@@ -697,13 +787,16 @@ int64_t device_slots()
 
 // workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | parked results 112 x batch doubles |
 //                    pre-pass 46 x batch doubles | hand-over slab 216 x slots doubles |
-//                    AA history AA_WORDS x slots floats (stage kernel only; the fused kernel uses TMEM)]
+//                    AA history AA_WORDS x slots words (stage kernel only; the fused kernel uses TMEM) |
+//                    FP32-phase export 166 x batch doubles | FP32 Q/rho 45 x 2 slots floats]
 size_t ws_bytes_for(int64_t slots, int64_t batch)
 {
     return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES) +
             (size_t)slots * cvx::HAND_DOUBLES) *
                sizeof(double) +
-           (size_t)slots * cvx::AA_WORDS * sizeof(float);
+           (size_t)slots * cvx::AA_WORDS * sizeof(float) +
+           // FP32 first phase: exported state per problem, Q/rho scratch of its 2x wider grid
+           (size_t)batch * cvx::WARM_DOUBLES * sizeof(double) + (size_t)slots * 2 * 45 * sizeof(float);
 }
 
 }  // namespace
@@ -742,6 +835,8 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(straggler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W_BYTES);
         if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(admm32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM32_BYTES);
+        if (e == cudaSuccess)
             e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_F_BYTES);
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
         attr_set = true;
@@ -764,9 +859,29 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e0 = cudaMemsetAsync(ctrl, 0, WS_HEADER_DOUBLES * sizeof(double), st);
     if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
+    const bool tm = d->timing != 0;
+    g_ev_n = 0;
+    mark(tm, 0, st);
     pre_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, st>>>(dd, o, pre);
-    solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, grace, slots);
     g_launches = 3;
+    const double* warm_in = nullptr;
+    if (d->fp32_iters > 0) {
+        // FP32 first phase, then its bases made orthonormal in FP64
+        double* warm = (double*)((uint32_t*)(slab + slots * cvx::HAND_DOUBLES) + slots * cvx::AA_WORDS);
+        float* qr32 = (float*)(warm + d->batch * cvx::WARM_DOUBLES);
+        const int64_t want32 = (d->batch + NT32 - 1) / NT32;
+        const int64_t blocks32 = want32 < slots / NT ? want32 : slots / NT;
+        mark(tm, 1, st);
+        admm32_kernel<<<(unsigned)blocks32, NT32, SMEM32_BYTES, st>>>(dd, o, ctrl, pre, warm, qr32, blocks32 * NT32,
+                                                                      d->fp32_iters);
+        mark(tm, 2, st);
+        ortho_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, st>>>(d->batch, warm);
+        warm_in = warm;
+        g_launches += 2;
+    }
+    mark(tm, 3, st);
+    solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm_in, grace,
+                                                                        slots);
     if (grace >= 0) {
         // at most one hand-over per lane of the first kernel: blocks * NT slab entries
         const int64_t max_strag = blocks * NT;
@@ -774,13 +889,34 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         int64_t wblocks = (max_strag + warps_per_cta - 1) / warps_per_cta;
         const int64_t wcap = (slots / NT) * 3;   // 3 CTAs of 72 KB per SM
         if (wblocks > wcap) wblocks = wcap;
+        mark(tm, 4, st);
         straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab);
-        solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, -1, slots);
-        g_launches = 5;
+        mark(tm, 5, st);
+        solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, -1,
+                                                                          slots);
+        g_launches += 2;
     }
+    mark(tm, 6, st);
     finish_kernel<<<(unsigned)((d->batch + NT_F - 1) / NT_F), NT_F, SMEM_F_BYTES, st>>>(dd, o, park);
+    mark(tm, -1, st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
+int cvxpnpl_b200_kernel_times(float* ms, int n)
+{
+    if (!ms || n < N_TIMED) return fail(-5, "kernel_times needs room for 7 floats");
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    if (g_ev_n < 2) return fail(-9, "the last solve on this thread was not timed (desc.timing = 0)");
+    cudaError_t e = cudaEventSynchronize(g_ev[g_ev_n - 1]);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    for (int i = 0; i + 1 < g_ev_n; ++i) {
+        float t = 0.f;
+        e = cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]);
+        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+        if (g_ev_slot[i] >= 0) ms[g_ev_slot[i]] = t;
+    }
     return 0;
 }
 

@@ -119,6 +119,121 @@ CVX_HD void problem_begin(const double* pre, const Opts& o, Arr<S> V, Arr<S> M, 
     st.converged = false;
 }
 
+// ---------------------------------------------------------------------------------
+// FP32 first phase (BASELINE.json configs[3]: "fp32 ADMM + fp64 extraction").  The
+// DR iteration is self-correcting -- any M is a valid state -- so the iterations that
+// only have to bring a problem from the cold start into the linear tail (||X - Z||_F
+// from ~50 down to 0.05, about 45 of the ~70 iterations, no Anderson steps yet) can run
+// in FP32: twice the FMA rate, half the shared memory per problem (so 256 instead of
+// 128 problems per SM and two warps per scheduler instead of one).  The FP32 kernel
+// exports (M, V, lambda, iteration count) per problem as doubles (WARM_DOUBLES); V is
+// re-orthonormalised in FP64 (ortho_kernel; rotations preserve whatever V'V is, so an
+// FP32-orthogonal basis would cap the accuracy at 1e-7 for good) and the FP64 solver
+// continues from there to the full tolerance with Anderson acceleration.
+// ---------------------------------------------------------------------------------
+constexpr int WARM_DOUBLES = 166;   // M 55 | V 100 | lambda 10 | iterations
+
+template <int S, class QRT>
+CVX_HD void problem_begin32(const double* pre, const Opts& o, ArrT<S, float> V, ArrT<S, float> M, ArrT<S, float> L,
+                            QRT QR)
+{
+#pragma unroll 5
+    for (int e = 0; e < 45; ++e) QR[e] = (float)pre[e];
+    const float s2 = (float)(o.sigma * o.sigma);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.f : 0.f;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) M[sidx(i, j)] = (i == j) ? (i == 9 ? s2 : 1.f / 3.f) : 0.f;
+        L[i] = (i == 9) ? s2 : 1.f / 3.f;
+    }
+}
+
+// one FP32 DR iteration + basis change + warm-started sweep; returns the squared residual
+template <int S, class QRT>
+CVX_HD float pass32(const Opts& o, ArrT<S, float> V, ArrT<S, float> M, ArrT<S, float> T, ArrT<S, float> L, QRT QR)
+{
+    float z[55];
+    const float res = f32::dr_step(M, V, L, T, QR, (float)o.alpha, (float)(1.0 / o.sigma), (float)o.rowk, z);
+    f32::rotate_into_basis(M, V, T);
+    float t[55];
+#pragma unroll
+    for (int e = 0; e < 55; ++e) t[e] = T[e];
+#pragma unroll 1
+    for (int s = 0; s < o.sweeps; ++s) f32::jacobi_sweep_reg(t, V);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) L[j] = t[sidx(j, j)];
+    return res;
+}
+
+template <int S>
+CVX_HD void problem_export32(ArrT<S, float> V, ArrT<S, float> M, ArrT<S, float> L, int it, double* w)
+{
+#pragma unroll 5
+    for (int e = 0; e < 55; ++e) w[e] = (double)M[e];
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) w[55 + e] = (double)V[e];
+#pragma unroll 2
+    for (int e = 0; e < 10; ++e) w[155 + e] = (double)L[e];
+    w[165] = (double)it;
+}
+
+// modified Gram-Schmidt on the columns of the exported eigenbasis, in FP64 (the basis
+// is held in registers: every loop is unrolled, all indices are compile-time)
+CVX_HD void warm_orthonormalise(double* w)
+{
+    double V[100];
+#pragma unroll
+    for (int e = 0; e < 100; ++e) V[e] = w[55 + e];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            if (k >= j) continue;
+            double dt = 0;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) dt = fma(V[i * 10 + j], V[i * 10 + k], dt);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) V[i * 10 + j] = fma(-dt, V[i * 10 + k], V[i * 10 + j]);
+        }
+        double n = 0;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) n = fma(V[i * 10 + j], V[i * 10 + j], n);
+        n = 1.0 / sqrt(n);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) V[i * 10 + j] *= n;
+    }
+#pragma unroll
+    for (int e = 0; e < 100; ++e) w[55 + e] = V[e];
+}
+
+// FP64 solver picks up a problem the FP32 phase has brought into the tail
+template <int S, class QRT>
+CVX_HD void problem_begin_warm(const double* pre, const double* w, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR,
+                               LaneState& st)
+{
+#pragma unroll 5
+    for (int e = 0; e < 45; ++e) QR[e] = pre[e];
+    const double rho = pre[45];
+#pragma unroll 5
+    for (int e = 0; e < 55; ++e) M[e] = w[e];
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) V[e] = w[55 + e];
+#pragma unroll 2
+    for (int e = 0; e < 10; ++e) L[e] = w[155 + e];
+    st.rho = rho;
+    st.dobj = 0.0;
+    st.phase = 0;
+    st.it = (int32_t)w[165];
+    aa_reset(st.aa);
+    st.res_prev = 1e300;
+    st.finite = isfinite(rho);
+    st.iterating = st.finite && st.it < o.max_iters;
+    if (st.finite && !st.iterating) st.phase = 1;
+    st.converged = false;
+}
+
 // One loop body serves both the DR iterations (one warm-started sweep each) and the
 // final passes that drive the eigen-decomposition of the last iterate to full
 // convergence, so the sweep code exists once.  Returns true when done.

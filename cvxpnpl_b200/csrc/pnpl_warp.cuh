@@ -210,6 +210,20 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
     unpack_idx(lane, er[0], ec[0]);
     unpack_idx(lane + 32 < 55 ? lane + 32 : 0, er[1], ec[1]);
     const int np = lane + 32 < 55 ? 2 : 1;
+    // pivot pairs of this lane's work items, all nine rounds, four bits each:
+    // T block (pa, qa) x (pb, qb); V items rows lane / 5 (pair pb, qb) and (lane + 32) / 5 (pair p1, q1)
+    uint32_t pk[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        int pa, qa, pb, qb, p1, q1;
+        round_pair(r, lane < 25 ? lane / 5 : 0, pa, qa);
+        round_pair(r, lane % 5, pb, qb);
+        round_pair(r, (lane + 32) % 5, p1, q1);
+        pk[r] = (uint32_t)pa | ((uint32_t)qa << 4) | ((uint32_t)pb << 8) | ((uint32_t)qb << 12) | ((uint32_t)p1 << 16) |
+                ((uint32_t)q1 << 20);
+    }
+    const int ka = lane < 25 ? lane / 5 : 0, kb = lane % 5, k1 = (lane + 32) % 5;
+    const int i0 = lane / 5, i1 = (lane + 32) / 5;
     uint32_t mask = 0u;
     bool have_prev = false;
     int wslot = 0;
@@ -217,18 +231,24 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
     converged = false;
     for (;;) {
         // ---- 1. Z = V max(L,0) V',  W = 2 Z - M - Q/rho  (W into X) -------------------
-        _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
-            const int r = er[q], c = ec[q];
-            double z = 0.0;
+        {
+            double lp[10];
 #pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const double l = S.L[j];
-                if (l > 0.0) z = fma(l * S.V[r * 10 + j], S.V[c * 10 + j], z);   // warp-uniform branch
+            for (int j = 0; j < 10; ++j) lp[j] = fmax(S.L[j], 0.0);
+            _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+                const int r = er[q], c = ec[q];
+                double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 10; j += 2) {
+                    z0 = fma(lp[j] * S.V[r * 10 + j], S.V[c * 10 + j], z0);
+                    z1 = fma(lp[j + 1] * S.V[r * 10 + j + 1], S.V[c * 10 + j + 1], z1);
+                }
+                const double z = z0 + z1;
+                const double w = 2.0 * z - S.M[r * 10 + c] - S.Q[r * 10 + c];
+                S.Z[r * 10 + c] = z;
+                S.X[r * 10 + c] = w;
+                S.X[c * 10 + r] = w;
             }
-            const double w = 2.0 * z - S.M[r * 10 + c] - S.Q[r * 10 + c];
-            S.Z[r * 10 + c] = z;
-            S.X[r * 10 + c] = w;
-            S.X[c * 10 + r] = w;
         }
         __syncwarp();
         // ---- 2. X = P_aff(W): one lane per equality group (15 triples, 9 diagonal entries,
@@ -386,23 +406,21 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
         // ---- 6. one Jacobi sweep: 9 rounds of 5 disjoint rotations.  Round: lanes 0..4
         //         compute (c, s); then 25 lanes update one 2x2 block of T each
         //         (T' = J'TJ, blocks are disjoint -> in place) and all lanes rotate rows of V.
-#pragma unroll 1
+#pragma unroll 1   // rolled: measured faster than nine unrolled copies (pk then lives in local memory)
         for (int round = 0; round < 9; ++round) {
+            const int pa = pk[round] & 15, qa = (pk[round] >> 4) & 15, pb = (pk[round] >> 8) & 15,
+                      qb = (pk[round] >> 12) & 15, p1 = (pk[round] >> 16) & 15, q1 = (pk[round] >> 20) & 15;
             if (lane < 5) {
-                int p, q;
-                round_pair(round, lane, p, q);
+                // lane k < 5 owns pair k = (pb, qb)
                 double c, s, tn;
-                jacobi_cs(S.T[p * 10 + p], S.T[q * 10 + q], S.T[q * 10 + p], c, s, tn);
+                jacobi_cs(S.T[pb * 11], S.T[qb * 11], S.T[qb * 10 + pb], c, s, tn);
                 S.cs[2 * lane] = c;
                 S.cs[2 * lane + 1] = s;
             }
             __syncwarp();
+            const double cb = S.cs[2 * kb], sb = S.cs[2 * kb + 1];
             if (lane < 25) {
-                const int ka = lane / 5, kb = lane - 5 * ka;
-                int pa, qa, pb, qb;
-                round_pair(round, ka, pa, qa);
-                round_pair(round, kb, pb, qb);
-                const double ca = S.cs[2 * ka], sa = S.cs[2 * ka + 1], cb = S.cs[2 * kb], sb = S.cs[2 * kb + 1];
+                const double ca = S.cs[2 * ka], sa = S.cs[2 * ka + 1];
                 const double b00 = S.T[pa * 10 + pb], b01 = S.T[pa * 10 + qb], b10 = S.T[qa * 10 + pb],
                              b11 = S.T[qa * 10 + qb];
                 const double y00 = ca * b00 - sa * b10, y01 = ca * b01 - sa * b11;
@@ -413,14 +431,16 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
                 S.T[qa * 10 + pb] = dg ? 0.0 : y10 * cb - y11 * sb;
                 S.T[qa * 10 + qb] = y10 * sb + y11 * cb;
             }
-            for (int v = lane; v < 50; v += 32) {
-                const int i = v / 5, k = v - 5 * i;
-                int p, q;
-                round_pair(round, k, p, q);
-                const double c = S.cs[2 * k], s = S.cs[2 * k + 1];
-                const double vp = S.V[i * 10 + p], vq = S.V[i * 10 + q];
-                S.V[i * 10 + p] = fma(c, vp, -s * vq);
-                S.V[i * 10 + q] = fma(s, vp, c * vq);
+            {
+                const double vp = S.V[i0 * 10 + pb], vq = S.V[i0 * 10 + qb];
+                S.V[i0 * 10 + pb] = fma(cb, vp, -sb * vq);
+                S.V[i0 * 10 + qb] = fma(sb, vp, cb * vq);
+            }
+            if (lane < 18) {
+                const double c = S.cs[2 * k1], s = S.cs[2 * k1 + 1];
+                const double vp = S.V[i1 * 10 + p1], vq = S.V[i1 * 10 + q1];
+                S.V[i1 * 10 + p1] = fma(c, vp, -s * vq);
+                S.V[i1 * 10 + q1] = fma(s, vp, c * vq);
             }
             __syncwarp();
         }

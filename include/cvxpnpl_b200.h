@@ -81,6 +81,11 @@ typedef struct cvxpnpl_b200_desc {
     /* ---- scratch ---- */
     double* workspace;      /* cvxpnpl_b200_workspace_bytes(batch) bytes */
     size_t workspace_bytes;
+    /* ---- precision ---- */
+    int32_t fp32_iters;     /* 0: FP64 ADMM throughout (BASELINE.json configs[1], [2]).  > 0: "fp32 ADMM + fp64
+                               extraction" (configs[3]): the iterations that bring a problem into the linear
+                               tail run in FP32 (at most this many), the FP64 solver finishes to `eps` */
+    int32_t timing;         /* != 0: record CUDA events between the kernels of `solve` (cvxpnpl_b200_kernel_times) */
 } cvxpnpl_b200_desc;
 
 /* library version string, e.g. "cvxpnpl_b200 0.1.0 (sm_100a)" */
@@ -96,6 +101,11 @@ size_t cvxpnpl_b200_workspace_bytes(int64_t batch);
  * success, a negative value for bad arguments, a positive cudaError_t otherwise.
  * `stream` is a cudaStream_t.  Asynchronous. */
 int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* desc, void* stream);
+
+/* Device time of each kernel of the last `solve` issued by this host thread with
+ * desc.timing != 0, in ms: pre, admm32, ortho, solve_fused, straggler, resume, finish
+ * (0 for kernels that were not launched).  Synchronises on the last event. */
+int cvxpnpl_b200_kernel_times(float* ms, int n);
 
 /* Stage: correspondences -> Q [B,9,9] (= A'A of cvxpnpl.py:475) and Bmat [B,3,9]
  * (cvxpnpl.py:623).  Uses the problem fields of desc only. */

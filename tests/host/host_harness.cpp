@@ -4,6 +4,7 @@
 // (`-m "not gpu"`) where no GPU exists.  It is NOT part of the product, is never
 // loaded by cvxpnpl_b200/, and is not a fallback: the product library fails loudly
 // without CUDA.
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -13,7 +14,7 @@
 extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
                           const double* pts_2d, const double* pts_3d, const double* line_2d,
                           const double* line_3d, double eps, int max_iters, int sweeps, double rho_rel,
-                          double alpha, double sigma, int anderson, int variant, double* R, double* t, int32_t* n_poses, int32_t* status,
+                          double alpha, double sigma, int anderson, int variant, int fp32_iters, double* R, double* t, int32_t* n_poses, int32_t* status,
                           int32_t* iters, double* obj, double* Z)
 {
     cvx::Opts o;
@@ -38,6 +39,35 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
         pr.n_pts = n_pts;
         pr.n_lines = n_lines;
         cvx::Result rs;
+        if (fp32_iters > 0) {
+            // "fp32 ADMM" first phase, exactly as admm32_kernel / ortho_kernel / problem_begin_warm do it
+            double pre[cvx::PRE_DOUBLES], warm[cvx::WARM_DOUBLES];
+            cvx::assemble_scaled(pr, o, pre);
+            std::vector<float> Vf(100), Mf(56), Tf(56), Lf(10), qf(45);
+            cvx::ArrT<1, float> aV{Vf.data()}, aM{Mf.data()}, aT{Tf.data()}, aL{Lf.data()}, aq{qf.data()};
+            cvx::problem_begin32(pre, o, aV, aM, aL, aq);
+            int it = 0;
+            if (std::isfinite(pre[45]))
+                for (;;) {
+                    const float res = cvx::pass32(o, aV, aM, aT, aL, aq);
+                    ++it;
+                    if (!(res > (float)o.aa_on2) || it >= fp32_iters) break;
+                }
+            cvx::problem_export32(aV, aM, aL, it, warm);
+            cvx::warm_orthonormalise(warm);
+            cvx::LaneState st;
+            cvx::Arr<1> dV{V.data()}, dM{M.data()}, dT{T.data()}, dL{L.data()}, dq{qr.data()};
+            cvx::problem_begin_warm(pre, warm, o, dV, dM, dL, dq, st);
+            const cvx::HistMem H{hist.data(), 1};
+            int wslot = 0;
+            for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+                const bool want = cvx::pass_dr(o, dV, dM, dT, dL, dq, st);
+                if (want) cvx::aa_step(dM, dT, H, st.aa, want, wslot, (float)st.res_prev);
+                wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
+                if (cvx::pass_eig(o, dV, dM, dT, dL, dq, st)) break;
+            }
+            cvx::problem_finish(pr, o, dV, dM, dT, dL, dq, st, R + b * 36, t + b * 12, Z ? Z + b * 100 : nullptr, rs);
+        } else
         cvx::solve_problem(pr, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{M.data()}, cvx::Arr<1>{T.data()},
                            cvx::Arr<1>{L.data()}, cvx::Arr<1>{qr.data()}, cvx::HistMem{hist.data(), 1},
                            R + b * 36, t + b * 12, Z ? Z + b * 100 : nullptr, rs);

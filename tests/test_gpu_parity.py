@@ -420,3 +420,32 @@ def test_straggler_warp_path_matches_thread_path(cb, n_pts, n_lines):
     ia, iw = a.iters.cpu().numpy()[ok], w.iters.cpu().numpy()[ok]
     # the hand-over only restarts the Anderson history: similar iteration counts
     assert np.median(iw) <= 1.3 * np.median(ia) + 10
+
+
+@pytest.mark.parametrize("n_pts,n_lines", [(0, 6), (8, 4)])
+def test_fp32_admm_matches_oracle(cb, n_pts, n_lines):
+    """BASELINE.json configs[3]: fp32 ADMM + fp64 extraction (PnL, 6 lines) -- and the
+    same switch on the PnPL configuration.  Against the CPU oracle on identical inputs,
+    north-star tolerance; and against the pure FP64 path on a larger batch."""
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    B = 4000
+    d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=91)
+    m = _solve(cb, d, n_pts, n_lines, admm_dtype="f32")
+    a = _solve(cb, d, n_pts, n_lines)
+    assert m.launches == a.launches + 2     # admm32_kernel + ortho_kernel really ran
+    sm, sa = (m.status & 0xFF).cpu().numpy(), (a.status & 0xFF).cpu().numpy()
+    ok = (sm == 0) & (sa == 0) & (m.n_poses.cpu().numpy() == 1) & (a.n_poses.cpu().numpy() == 1)
+    assert ok.mean() > 0.95
+    Rm, tm = m.R[:, 0].cpu().numpy(), m.t[:, 0].cpu().numpy()
+    Ra, ta = a.R[:, 0].cpu().numpy(), a.t[:, 0].cpu().numpy()
+    ang = synth.rotation_angle(Ra[ok], Rm[ok])
+    terr = np.linalg.norm(ta[ok] - tm[ok], axis=1) / np.linalg.norm(ta[ok], axis=1)
+    assert ang.max() <= ROT_TOL and terr.max() <= T_TOL, (ang.max(), terr.max())
+    checked = 0
+    for i in np.flatnonzero(ok)[:6]:
+        Ro, to = _oracle_call(orc, d, i, n_pts, n_lines, max_iters=100000)[0]
+        assert synth.rotation_angle(Ro, Rm[i]) <= ROT_TOL
+        assert np.linalg.norm(to - tm[i]) / np.linalg.norm(to) <= T_TOL
+        checked += 1
+    assert checked == 6

@@ -59,3 +59,27 @@ def test_quartic_real_parts():
         ref = np.sort(np.real(np.roots(c[::-1])))
         got = np.sort(harness.quartic(c))
         assert np.abs(got - ref).max() / max(1.0, np.abs(ref).max()) < 1e-8
+
+
+@pytest.mark.parametrize("n_pts,n_lines", [(0, 6), (8, 4)])
+def test_host_fp32_first_phase(n_pts, n_lines):
+    """"fp32 ADMM + fp64 extraction" (BASELINE.json configs[3]): FP32 iterations into the
+    tail, FP64 re-orthonormalisation, FP64 iterations to eps.  Same poses as the pure
+    FP64 solve (1e-6 rad / 1e-6 relative is the north-star tolerance; the two agree far
+    better), and the SDP optimum is still certified by the KKT conditions."""
+    B = 40
+    d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=33)
+    a = harness.solve(d)
+    m = harness.solve(d, fp32_iters=400)
+    ok = (a["status"] & 0xFF == 0) & (m["status"] & 0xFF == 0)
+    assert ok.mean() > 0.9 and (a["n_poses"][ok] == 1).all() and (m["n_poses"][ok] == 1).all()
+    ang = synth.rotation_angle(a["R"][ok, 0], m["R"][ok, 0])
+    terr = np.linalg.norm(a["t"][ok, 0] - m["t"][ok, 0], axis=1) / np.linalg.norm(a["t"][ok, 0], axis=1)
+    assert ang.max() < 1e-7 and terr.max() < 1e-7
+    # part of the iterations really ran in FP32, and the total is not inflated
+    assert np.median(m["iters"][ok]) <= 1.15 * np.median(a["iters"][ok]) + 5
+    # equality residual and PSD-ness of the returned Z
+    for i in np.flatnonzero(ok)[:5]:
+        Z = m["Z"][i]
+        assert abs(Z[9, 9] - 1.0) < 1e-8 and np.linalg.eigvalsh(Z).min() > -1e-9
+        assert abs(np.trace(Z[:9, :9]) - 3.0) < 1e-8

@@ -12,6 +12,7 @@ ap.add_argument("--n-lines", type=int, default=4)
 ap.add_argument("--batch", type=int, default=100000)
 ap.add_argument("--calls", type=int, default=2)
 ap.add_argument("--handoff", type=int, default=0)
+ap.add_argument("--admm", default="f64")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 d = synth.make_batch(a.batch, a.n_pts, a.n_lines, noise=1.0, seed=42)
@@ -24,6 +25,6 @@ if a.n_lines:
 ws = cb.Workspace(a.batch, dev)
 out = None
 for _ in range(a.calls):
-    out = cb.solve_batched(K, **args, workspace=ws, out=out, handoff=a.handoff)
+    out = cb.solve_batched(K, **args, workspace=ws, out=out, handoff=a.handoff, admm_dtype=a.admm)
 torch.cuda.synchronize()
 print("iters mean", float(out.iters.float().mean()), "max", int(out.iters.max()))
