@@ -305,7 +305,7 @@ namespace cvx {
 // On entry M already holds M_k + g_k and G holds g_k; on exit M holds M_{k+1}.
 // ---------------------------------------------------------------------------------
 constexpr int AA_M = 7;
-constexpr double AA_RES2_ON = 0.05 * 0.05;   // accelerate only once ||X - Z||_F < 0.05 (|Z| ~ 4)
+constexpr double AA_RES2_ON = 0.15 * 0.15;   // accelerate only once ||X - Z||_F < 0.15 (|Z| ~ 4)
 #ifndef CVX_AA_MAXSTEP2
 #define CVX_AA_MAXSTEP2 100.f
 #endif

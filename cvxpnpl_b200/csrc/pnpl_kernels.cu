@@ -174,17 +174,20 @@ __device__ __forceinline__ cvx::Problem problem_at(const cvxpnpl_b200_desc& d, i
 // of the batch (median ~300, tail to 2500) costs no idle lanes.
 // ---------------------------------------------------------------------------------
 // control words at the head of the workspace (unsigned long long each)
-enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3, CTRL_NEXT32 = 4 };
+enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3, CTRL_NEXT32 = 4, CTRL_ACTIVE = 5 };
 
 // RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
 //   is empty, a lane whose problem is still in its DR loop `grace` passes later hands it
-//   over to the warp-per-problem kernel (pnpl_warp.cuh) through a slab entry and leaves.
+//   over to the warp-per-problem kernel (pnpl_warp.cuh) through a slab entry and leaves --
+//   provided no more than `handoff_max` problems are still iterating on the whole GPU
+//   (one warp of the straggler kernel each): the warp mapping buys latency with ~8x the
+//   issue slots per iteration, so while many problems are alive this kernel keeps them.
 // RESUME = true: second visit for the handed-over problems, whose DR loop has been
 //   finished by straggler_kernel: polish the eigen-decomposition, park.
 template <bool RESUME>
 __global__ void __launch_bounds__(NT, 1)
 solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const double* pre, double* park,
-                   double* slab, const double* warm, int grace, int64_t ws_stride)
+                   double* slab, const double* warm, int grace, int handoff_max, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
@@ -211,6 +214,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
     int64_t b = -1;
     bool exhausted = false;
     int drain = 0;   // passes since this lane saw the queue empty
+    bool counted = false;   // this lane's problem is counted in ctrl[CTRL_ACTIVE]
     const unsigned long long n_work = RESUME ? ctrl[CTRL_NSTRAG] : (unsigned long long)d.batch;
     cvx::LaneState st;
     st.finite = false;
@@ -245,10 +249,18 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
         if (!RESUME && grace >= 0 && b >= 0 && st.iterating) {
             // hand-over: the queue is empty (nothing left to steal), this problem is still in
             // its DR loop `grace` passes later -> the warp-per-problem kernel finishes it
-            if (drain > 0 || *(volatile unsigned long long*)(ctrl + CTRL_NEXT) >= n_work) ++drain;
-            if (drain > grace) {
+            if (drain > 0 || *(volatile unsigned long long*)(ctrl + CTRL_NEXT) >= n_work) {
+                if (!counted) {
+                    atomicAdd(ctrl + CTRL_ACTIVE, 1ULL);
+                    counted = true;
+                }
+                ++drain;
+            }
+            if (drain > grace && *(volatile unsigned long long*)(ctrl + CTRL_ACTIVE) <= (unsigned long long)handoff_max) {
                 const unsigned long long k = atomicAdd(ctrl + CTRL_NSTRAG, 1ULL);
                 cvx::problem_handoff(V, M, L, QR, st, b, slab + k * cvx::HAND_DOUBLES);
+                atomicAdd(ctrl + CTRL_ACTIVE, ~0ULL);   // -1
+                counted = false;
                 b = -1;
                 exhausted = true;
             }
@@ -264,6 +276,10 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
                 // park the eigen-decomposition; poses are extracted by finish_kernel
                 cvx::problem_park(V, L, st, park + b * cvx::PARK_DOUBLES, d.iters + b);
                 b = -1;
+            }
+            if (counted && (b < 0 || !st.iterating)) {   // DR loop over: no longer a hand-over candidate
+                atomicAdd(ctrl + CTRL_ACTIVE, ~0ULL);
+                counted = false;
             }
         }
     }
@@ -388,14 +404,22 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
 }
 
 // ---------------------------------------------------------------------------------
-// Pre-pass kernel: correspondences -> Q/rho and rho per problem (46 doubles), one
-// thread per problem, lane-parallel.
+// Pre-pass kernel: correspondences -> Q/rho, rho and the eigen-decomposition of the DR
+// start point (156 doubles per problem), one thread per problem, lane-parallel.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre)
+constexpr int NT_P = 64;
+constexpr size_t SMEM_P_BYTES = (size_t)NT_P * 155 * sizeof(double);   // V 100 + T 55
+__global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre)
 {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * NT_P + tid;
     if (b >= d.batch) return;
-    cvx::assemble_scaled(problem_at(d, b), o, pre + b * cvx::PRE_DOUBLES);
+    cvx::Arr<NT_P> V{smem + tid};
+    cvx::Arr<NT_P> T{smem + (size_t)100 * NT_P + tid};
+    double* out = pre + b * cvx::PRE_DOUBLES;
+    cvx::assemble_scaled(problem_at(d, b), o, out);
+    cvx::start_decomposition(out, o, V, T);   // eigen-decomposition of the start point (cold Jacobi)
 }
 
 // ---------------------------------------------------------------------------------
@@ -646,11 +670,24 @@ solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, uint32_t* hist, i
         const double ir = 1.0 / st.rho;
         for (int i = 0; i < 9; ++i)
             for (int j = 0; j <= i; ++j) qr[cvx::sidx(i, j)] = (0.5 * (Qi[9 * i + j] + Qi[9 * j + i])) * ir;
+        // start point M0 = blkdiag(I/3 - kappa Q/rho, sigma^2) and its eigen-decomposition
+        // (this stage kernel is lane-parallel, so the cold Jacobi runs right here)
         for (int i = 0; i < 10; ++i) {
             for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
-            for (int j = 0; j <= i; ++j) M[cvx::sidx(i, j)] = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
-            L[i] = (i == 9) ? o.sigma * o.sigma : 1.0 / 3.0;
+            for (int j = 0; j <= i; ++j) {
+                double m = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
+                if (i < 9 && st.finite) m = fma(-o.kappa, (double)qr[cvx::sidx(i, j)], m);
+                M[cvx::sidx(i, j)] = m;
+                T[cvx::sidx(i, j)] = m;
+            }
         }
+        if (st.finite)
+            for (int s = 0; s < 10; ++s) {
+                double dg = 0;
+                for (int j = 0; j < 10; ++j) dg = fma(T[cvx::sidx(j, j)], T[cvx::sidx(j, j)], dg);
+                if (!(cvx::jacobi_sweep(T, V) > 1e-26 * dg)) break;
+            }
+        for (int j = 0; j < 10; ++j) L[j] = T[cvx::sidx(j, j)];
         int wslot = 0;
         for (int guard = 0; guard < o.max_iters + 40; ++guard) {
             const bool want = cvx::pass_dr(o, V, M, T, L, qr, st);
@@ -765,6 +802,7 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     o.anderson = d->anderson >= 0;
     o.aa_on2 = cvx::AA_RES2_ON;
     o.rowk = (d->variant == 1) ? 0.0 : 1.0;
+    o.kappa = cvx::DUAL_GUESS;
     o.max_iters = d->max_iters > 0 ? d->max_iters : 2500;
     o.sweeps = d->sweeps > 0 ? d->sweeps : 1;
     return o;
@@ -835,6 +873,8 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(straggler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W_BYTES);
         if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_P_BYTES);
+        if (e == cudaSuccess)
             e = cudaFuncSetAttribute(admm32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM32_BYTES);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_F_BYTES);
@@ -862,7 +902,7 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     const bool tm = d->timing != 0;
     g_ev_n = 0;
     mark(tm, 0, st);
-    pre_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, st>>>(dd, o, pre);
+    pre_kernel<<<(unsigned)((d->batch + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(dd, o, pre);
     g_launches = 3;
     const double* warm_in = nullptr;
     if (d->fp32_iters > 0) {
@@ -879,20 +919,20 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         warm_in = warm;
         g_launches += 2;
     }
+    // straggler grid: one warp per handed-over problem, at most 2 CTAs of 8 warps per SM
+    const int64_t warps_per_cta = NT_W / 32;
+    int64_t wblocks = (blocks * NT + warps_per_cta - 1) / warps_per_cta;   // at most one hand-over per lane
+    const int64_t wcap = (slots / NT) * 2;
+    if (wblocks > wcap) wblocks = wcap;
+    const int handoff_max = (int)(wblocks * warps_per_cta);
     mark(tm, 3, st);
     solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm_in, grace,
-                                                                        slots);
+                                                                        handoff_max, slots);
     if (grace >= 0) {
-        // at most one hand-over per lane of the first kernel: blocks * NT slab entries
-        const int64_t max_strag = blocks * NT;
-        const int64_t warps_per_cta = NT_W / 32;
-        int64_t wblocks = (max_strag + warps_per_cta - 1) / warps_per_cta;
-        const int64_t wcap = (slots / NT) * 3;   // 3 CTAs of 72 KB per SM
-        if (wblocks > wcap) wblocks = wcap;
         mark(tm, 4, st);
         straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab);
         mark(tm, 5, st);
-        solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, -1,
+        solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, -1, 0,
                                                                           slots);
         g_launches += 2;
     }

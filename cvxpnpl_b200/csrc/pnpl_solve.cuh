@@ -18,6 +18,7 @@ struct Opts {
     bool anderson;    // Anderson acceleration of the DR iteration (see aa_step)
     double aa_on2;    // squared residual below which Anderson acceleration is active
     double rowk;      // 1: reference SDP (22 equalities); 0: "rc" ablation (16 equalities)
+    double kappa;     // dual guess of the start point: U0 = kappa Q/rho (see start_decomposition)
 };
 
 struct Problem {
@@ -69,7 +70,10 @@ struct LaneState {
 // Assembly for one problem into 46 doubles: Q/rho (45, packed) and rho.  Run by a
 // lane-parallel pre-pass kernel (pre_kernel) so that the persistent solver's
 // problem_begin -- which executes with a single active lane -- only has to copy.
-constexpr int PRE_DOUBLES = 46;
+// ... followed by the eigen-decomposition of the start point (V 100, lambda 10): 156 doubles.
+constexpr int PRE_DOUBLES = 156;
+constexpr int PRE_V = 46, PRE_L = 146;
+constexpr double DUAL_GUESS = 0.75;
 
 template <class QOut>
 CVX_HD void assemble_scaled(const Problem& pr, const Opts& o, QOut out)
@@ -92,22 +96,68 @@ CVX_HD void assemble_scaled(const Problem& pr, const Opts& o, QOut out)
     out[45] = finite ? rho : nan("");
 }
 
+// Start point.  Primal: Z0 = blkdiag(I/3, sigma^2), feasible for the diagonal equalities.
+// Dual: U0 = kappa Q/rho -- at the optimum rho U = Q - sum_k y_k P_k, so the cost matrix
+// itself is the natural first guess (measured on seeded batches with kappa = 0.75: mean DR
+// iterations 70.9 -> 60.5 on PnPL 8+4, 80.5 -> 62.2 on PnP-8, 169 -> 136 on PnL-6; kappa = 1
+// is worse than none).  The DR state is M0 = Z0 - U0 = blkdiag(I/3 - kappa Q/rho, sigma^2);
+// the solver needs its eigen-decomposition, which is that of Q: cold cyclic Jacobi, run
+// lane-parallel in the pre-pass kernel (it would serialise inside the persistent kernel).
+// `pre` holds Q/rho and rho on entry (assemble_scaled) and receives V, lambda.  V and T
+// are strided work arrays.
+template <int S>
+CVX_HD void start_decomposition(double* pre, const Opts& o, Arr<S> V, Arr<S> T)
+{
+    const bool finite = isfinite(pre[45]);
+#pragma unroll 1
+    for (int i = 0; i < 10; ++i) {
+#pragma unroll 1
+        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+        for (int j = 0; j <= i; ++j) {
+            double m = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
+            if (i < 9 && finite) m = fma(-o.kappa, pre[sidx(i, j)], m);
+            T[sidx(i, j)] = m;
+        }
+    }
+    if (finite && o.kappa != 0.0) {
+#pragma unroll 1
+        for (int s = 0; s < 10; ++s) {
+            double dg = 0;
+#pragma unroll 1
+            for (int j = 0; j < 10; ++j) dg = fma(T[sidx(j, j)], T[sidx(j, j)], dg);
+            if (!(jacobi_sweep(T, V) > 1e-26 * dg)) break;
+        }
+    }
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) pre[PRE_V + e] = V[e];
+#pragma unroll 2
+    for (int j = 0; j < 10; ++j) pre[PRE_L + j] = T[sidx(j, j)];
+}
+
 template <int S, class QRT>
 CVX_HD void problem_begin(const double* pre, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
 {
-#pragma unroll 5
-    for (int e = 0; e < 45; ++e) QR[e] = pre[e];
     const double rho = pre[45];
     const bool finite = isfinite(rho);
-    // start: Z0 = blkdiag(I/3, 1) (feasible for the diagonal block), U0 = 0
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-#pragma unroll
-        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int j = 0; j <= i; ++j) M[sidx(i, j)] = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
-        L[i] = (i == 9) ? o.sigma * o.sigma : 1.0 / 3.0;
-    }
+    // M0 = blkdiag(I/3 - kappa Q/rho, sigma^2) and its eigen-decomposition from the pre-pass
+#pragma unroll 1
+    for (int i = 0; i < 10; ++i)
+#pragma unroll 1
+        for (int j = 0; j <= i; ++j) {
+            const int e = sidx(i, j);
+            double m = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
+            if (i < 9) {
+                const double q = pre[e];
+                QR[e] = q;
+                if (finite) m = fma(-o.kappa, q, m);
+            }
+            M[e] = m;
+        }
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) V[e] = pre[PRE_V + e];
+#pragma unroll 2
+    for (int j = 0; j < 10; ++j) L[j] = pre[PRE_L + j];
     st.rho = rho;
     st.dobj = 0.0;
     st.phase = 0;
@@ -137,17 +187,25 @@ template <int S, class QRT>
 CVX_HD void problem_begin32(const double* pre, const Opts& o, ArrT<S, float> V, ArrT<S, float> M, ArrT<S, float> L,
                             QRT QR)
 {
-#pragma unroll 5
-    for (int e = 0; e < 45; ++e) QR[e] = (float)pre[e];
-    const float s2 = (float)(o.sigma * o.sigma);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-#pragma unroll
-        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.f : 0.f;
-#pragma unroll
-        for (int j = 0; j <= i; ++j) M[sidx(i, j)] = (i == j) ? (i == 9 ? s2 : 1.f / 3.f) : 0.f;
-        L[i] = (i == 9) ? s2 : 1.f / 3.f;
-    }
+    const bool finite = isfinite(pre[45]);
+    const float s2 = (float)(o.sigma * o.sigma), kap = (float)o.kappa;
+#pragma unroll 1
+    for (int i = 0; i < 10; ++i)
+#pragma unroll 1
+        for (int j = 0; j <= i; ++j) {
+            const int e = sidx(i, j);
+            float m = (i == j) ? (i == 9 ? s2 : 1.f / 3.f) : 0.f;
+            if (i < 9) {
+                const float q = (float)pre[e];
+                QR[e] = q;
+                if (finite) m = fmaf(-kap, q, m);
+            }
+            M[e] = m;
+        }
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) V[e] = (float)pre[PRE_V + e];
+#pragma unroll 2
+    for (int j = 0; j < 10; ++j) L[j] = (float)pre[PRE_L + j];
 }
 
 // one FP32 DR iteration + basis change + warm-started sweep; returns the squared residual
@@ -452,6 +510,7 @@ CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
     LaneState st;
     double pre[PRE_DOUBLES];
     assemble_scaled(pr, o, pre);
+    start_decomposition(pre, o, V, T);
     problem_begin(pre, o, V, M, L, QR, st);
     int wslot = 0;
 #pragma unroll 1

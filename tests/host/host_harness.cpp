@@ -26,6 +26,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
     o.sigma = sigma > 0 ? sigma : 1.5;
     o.anderson = anderson != 0;
     o.rowk = variant == 1 ? 0.0 : 1.0;
+    o.kappa = cvx::DUAL_GUESS;
     o.aa_on2 = (anderson > 1) ? (1e-3 * anderson) * (1e-3 * anderson) : cvx::AA_RES2_ON;   // test hook: threshold in 1e-3 units
     std::vector<double> V(100), M(56), T(56), L(10), qr(45);   // T[55] = 0: zero pad for aa_step
     std::vector<uint32_t> hist(cvx::AA_WORDS, 0u);
@@ -43,6 +44,8 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
             // "fp32 ADMM" first phase, exactly as admm32_kernel / ortho_kernel / problem_begin_warm do it
             double pre[cvx::PRE_DOUBLES], warm[cvx::WARM_DOUBLES];
             cvx::assemble_scaled(pr, o, pre);
+            cvx::start_decomposition(pre, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{T.data()});
+            T[55] = 0.0;
             std::vector<float> Vf(100), Mf(56), Tf(56), Lf(10), qf(45);
             cvx::ArrT<1, float> aV{Vf.data()}, aM{Mf.data()}, aT{Tf.data()}, aL{Lf.data()}, aq{qf.data()};
             cvx::problem_begin32(pre, o, aV, aM, aL, aq);

@@ -20,7 +20,7 @@ for (npt, nl) in ((8, 4), (8, 0), (0, 6)):
         args.update(line_2d=torch.from_numpy(d["line_2d"]).to(dev), line_3d=torch.from_numpy(d["line_3d"]).to(dev))
     ws = cb.Workspace(B, dev)
     ref = None
-    for admm in ("f64", "f32"):
+    for admm in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("f64", "f32")):
         for grace in graces:
             out = None
             for _ in range(2):
