@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
 // start point (156 doubles per problem), one thread per problem, lane-parallel.
 // ---------------------------------------------------------------------------------
 constexpr int NT_P = 64;
-constexpr size_t SMEM_P_BYTES = (size_t)NT_P * 155 * sizeof(double);   // V 100 + T 55
+constexpr size_t SMEM_P_BYTES = (size_t)NT_P * 100 * sizeof(double);   // V (T stays in registers)
 __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre)
 {
     extern __shared__ double smem[];
@@ -416,10 +416,9 @@ __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, 
     const int64_t b = (int64_t)blockIdx.x * NT_P + tid;
     if (b >= d.batch) return;
     cvx::Arr<NT_P> V{smem + tid};
-    cvx::Arr<NT_P> T{smem + (size_t)100 * NT_P + tid};
     double* out = pre + b * cvx::PRE_DOUBLES;
     cvx::assemble_scaled(problem_at(d, b), o, out);
-    cvx::start_decomposition(out, o, V, T);   // eigen-decomposition of the start point (cold Jacobi)
+    cvx::start_decomposition(out, o, V);   // eigen-decomposition of the start point (cold Jacobi)
 }
 
 // ---------------------------------------------------------------------------------

@@ -103,61 +103,84 @@ CVX_HD void assemble_scaled(const Problem& pr, const Opts& o, QOut out)
 // is worse than none).  The DR state is M0 = Z0 - U0 = blkdiag(I/3 - kappa Q/rho, sigma^2);
 // the solver needs its eigen-decomposition, which is that of Q: cold cyclic Jacobi, run
 // lane-parallel in the pre-pass kernel (it would serialise inside the persistent kernel).
-// `pre` holds Q/rho and rho on entry (assemble_scaled) and receives V, lambda.  V and T
-// are strided work arrays.
+// `pre` holds Q/rho and rho on entry (assemble_scaled) and receives V, lambda.  V is a
+// strided work array.
 template <int S>
-CVX_HD void start_decomposition(double* pre, const Opts& o, Arr<S> V, Arr<S> T)
+CVX_HD void start_decomposition(double* pre, const Opts& o, Arr<S> V)
 {
     const bool finite = isfinite(pre[45]);
-#pragma unroll 1
+    double t[55];   // registers: every index below is a compile-time constant
+#pragma unroll
     for (int i = 0; i < 10; ++i) {
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j <= i; ++j) {
             double m = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
             if (i < 9 && finite) m = fma(-o.kappa, pre[sidx(i, j)], m);
-            T[sidx(i, j)] = m;
+            t[sidx(i, j)] = m;
         }
     }
     if (finite && o.kappa != 0.0) {
+        // the solver refines the decomposition by one warm-started sweep per iteration, so the
+        // cold start only has to get close: stop once the pivots seen by a sweep are below
+        // 1e-7 of the diagonal (the next sweep would square that)
 #pragma unroll 1
         for (int s = 0; s < 10; ++s) {
             double dg = 0;
-#pragma unroll 1
-            for (int j = 0; j < 10; ++j) dg = fma(T[sidx(j, j)], T[sidx(j, j)], dg);
-            if (!(jacobi_sweep(T, V) > 1e-26 * dg)) break;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) dg = fma(t[sidx(j, j)], t[sidx(j, j)], dg);
+            if (!(jacobi_sweep_reg(t, V) > 1e-14 * dg)) break;
         }
     }
 #pragma unroll 4
     for (int e = 0; e < 100; ++e) pre[PRE_V + e] = V[e];
-#pragma unroll 2
-    for (int j = 0; j < 10; ++j) pre[PRE_L + j] = T[sidx(j, j)];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) pre[PRE_L + j] = t[sidx(j, j)];
 }
 
 template <int S, class QRT>
 CVX_HD void problem_begin(const double* pre, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
 {
+    // Inside the persistent kernel this runs with ONE active lane while 31 wait, and the
+    // record is cold (L2 / HBM): issue the loads in large independent groups so their
+    // latencies overlap instead of adding up.
     const double rho = pre[45];
     const bool finite = isfinite(rho);
-    // M0 = blkdiag(I/3 - kappa Q/rho, sigma^2) and its eigen-decomposition from the pre-pass
-#pragma unroll 1
-    for (int i = 0; i < 10; ++i)
-#pragma unroll 1
-        for (int j = 0; j <= i; ++j) {
-            const int e = sidx(i, j);
-            double m = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
-            if (i < 9) {
-                const double q = pre[e];
-                QR[e] = q;
-                if (finite) m = fma(-o.kappa, q, m);
+    {
+        double q[45];
+#pragma unroll
+        for (int e = 0; e < 45; ++e) q[e] = pre[e];
+        // M0 = blkdiag(I/3 - kappa Q/rho, sigma^2)
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const int e = sidx(i, j);
+                double m = (i == j) ? (i == 9 ? o.sigma * o.sigma : 1.0 / 3.0) : 0.0;
+                if (i < 9) {
+                    QR[e] = q[e];
+                    if (finite) m = fma(-o.kappa, q[e], m);
+                }
+                M[e] = m;
             }
-            M[e] = m;
-        }
-#pragma unroll 4
-    for (int e = 0; e < 100; ++e) V[e] = pre[PRE_V + e];
-#pragma unroll 2
-    for (int j = 0; j < 10; ++j) L[j] = pre[PRE_L + j];
+    }
+    // ... and its eigen-decomposition from the pre-pass
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double v[50];
+#pragma unroll
+        for (int e = 0; e < 50; ++e) v[e] = pre[PRE_V + 50 * h + e];
+#pragma unroll
+        for (int e = 0; e < 50; ++e) V[50 * h + e] = v[e];
+    }
+    {
+        double l[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) l[j] = pre[PRE_L + j];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) L[j] = l[j];
+    }
     st.rho = rho;
     st.dobj = 0.0;
     st.phase = 0;
@@ -271,15 +294,34 @@ template <int S, class QRT>
 CVX_HD void problem_begin_warm(const double* pre, const double* w, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> L, QRT QR,
                                LaneState& st)
 {
-#pragma unroll 5
-    for (int e = 0; e < 45; ++e) QR[e] = pre[e];
+    // loads in large independent groups (one active lane, cold records: see problem_begin)
     const double rho = pre[45];
-#pragma unroll 5
-    for (int e = 0; e < 55; ++e) M[e] = w[e];
-#pragma unroll 4
-    for (int e = 0; e < 100; ++e) V[e] = w[55 + e];
-#pragma unroll 2
-    for (int e = 0; e < 10; ++e) L[e] = w[155 + e];
+    {
+        double q[45];
+#pragma unroll
+        for (int e = 0; e < 45; ++e) q[e] = pre[e];
+#pragma unroll
+        for (int e = 0; e < 45; ++e) QR[e] = q[e];
+    }
+    {
+        double m[55];
+#pragma unroll
+        for (int e = 0; e < 55; ++e) m[e] = w[e];
+#pragma unroll
+        for (int e = 0; e < 55; ++e) M[e] = m[e];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double v[55];
+#pragma unroll
+        for (int e = 0; e < 55; ++e) v[e] = w[55 + 55 * h + e];   // V (100) then lambda (10)
+#pragma unroll
+        for (int e = 0; e < 55; ++e) {
+            const int k = 55 * h + e;
+            if (k < 100) V[k] = v[e];
+            else L[k - 100] = v[e];
+        }
+    }
     st.rho = rho;
     st.dobj = 0.0;
     st.phase = 0;
@@ -510,7 +552,7 @@ CVX_HD void solve_problem(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M, 
     LaneState st;
     double pre[PRE_DOUBLES];
     assemble_scaled(pr, o, pre);
-    start_decomposition(pre, o, V, T);
+    start_decomposition(pre, o, V);
     problem_begin(pre, o, V, M, L, QR, st);
     int wslot = 0;
 #pragma unroll 1

@@ -44,8 +44,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
             // "fp32 ADMM" first phase, exactly as admm32_kernel / ortho_kernel / problem_begin_warm do it
             double pre[cvx::PRE_DOUBLES], warm[cvx::WARM_DOUBLES];
             cvx::assemble_scaled(pr, o, pre);
-            cvx::start_decomposition(pre, o, cvx::Arr<1>{V.data()}, cvx::Arr<1>{T.data()});
-            T[55] = 0.0;
+            cvx::start_decomposition(pre, o, cvx::Arr<1>{V.data()});
             std::vector<float> Vf(100), Mf(56), Tf(56), Lf(10), qf(45);
             cvx::ArrT<1, float> aV{Vf.data()}, aM{Mf.data()}, aT{Tf.data()}, aL{Lf.data()}, aq{qf.data()};
             cvx::problem_begin32(pre, o, aV, aM, aL, aq);
