@@ -278,6 +278,27 @@ namespace f32 {
 
 namespace cvx {
 
+// Rotation with an FP32 angle and an FP64 normalisation: tan(theta) from the textbook
+// formula in single precision (one MUFU square root and one reciprocal), then
+// c = 1 / sqrt(1 + t^2), s = t c in double.  The rotation is orthogonal to double precision
+// (which is what keeps V orthonormal); the pivot is annihilated only to ~1e-7 of its size
+// instead of exactly, which a warm-started solver that sweeps once per DR iteration does
+// not notice (the leftover is squared away by the next sweep).  Half the FP64 work of
+// jacobi_cs (one reciprocal square root instead of two): used where the rotation angles
+// are on the critical path (the warp-per-problem kernel, pnpl_warp.cuh).
+CVX_HD void jacobi_cs_fast(double app, double aqq, double apq, double& c, double& s)
+{
+    const double d = aqq - app, b2 = 2.0 * apq;
+    const double g = fma(d, d, b2 * b2);
+    const bool skip = !(fabs(apq) > 1e-18 * fabs(d)) || !(g > 1e-280);
+    const float df = (float)d, bf = (float)b2;
+    float tf = copysignf(bf, bf * df) / (fabsf(df) + sqrtf(fmaf(df, df, bf * bf)));
+    tf = fminf(fmaxf(tf, -1.f), 1.f);        // |theta| <= pi/4; also catches 0/0-free overflow to inf
+    const double t = skip || !(tf == tf) ? 0.0 : (double)tf;
+    c = cvx_rsqrt(fma(t, t, 1.0));
+    s = t * c;
+}
+
 // ---------------------------------------------------------------------------------
 // Anderson acceleration (type II, memory AA_M = 7) of the DR fixed-point iteration
 // M <- F(M), the accelerator SCS itself relies on.  With g_k = F(M_k) - M_k:

@@ -412,8 +412,8 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
                       qb = (pk[round] >> 12) & 15, p1 = (pk[round] >> 16) & 15, q1 = (pk[round] >> 20) & 15;
             if (lane < 5) {
                 // lane k < 5 owns pair k = (pb, qb)
-                double c, s, tn;
-                jacobi_cs(S.T[pb * 11], S.T[qb * 11], S.T[qb * 10 + pb], c, s, tn);
+                double c, s;
+                jacobi_cs_fast(S.T[pb * 11], S.T[qb * 11], S.T[qb * 10 + pb], c, s);
                 S.cs[2 * lane] = c;
                 S.cs[2 * lane + 1] = s;
             }
