@@ -122,7 +122,8 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
             Q, Bm = assemble_batched(K, pts_2d if have_p else None, pts_3d if have_p else None,
                                      line_2d if have_l else None, line_3d if have_l else None)
             Z, dobj, iters, status = solve_sdp_batched(Q, eps=eps, max_iters=max_iters, sweeps=sweeps, rho_rel=rho_rel,
-                                                       alpha=alpha, sigma=sigma, anderson=anderson)
+                                                       alpha=alpha, sigma=sigma, anderson=anderson,
+                                                       n_pts=pts_2d.shape[1] if have_p else 0)
             res = extract_batched(Z, Q, Bm, dobj, eps=eps)
             res.iters = iters
             # keep the solver's status (MAX_ITERS / NaN) where extraction itself succeeded
@@ -212,9 +213,11 @@ def assemble_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None):
     return Q, Bm
 
 
-def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True):
+def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True,
+                      n_pts=8):
     """Q [B,9,9] -> (Z [B,10,10], dobj [B], iters [B], status [B]); the scs.solve
-    call of cvxpnpl.py:478-492."""
+    call of cvxpnpl.py:478-492.  n_pts (points behind each Q) only selects the default
+    rho / sigma where they are left 0."""
     _require_cuda()
     lib = _lib.load()
     device = torch.device("cuda", torch.cuda.current_device())
@@ -227,6 +230,7 @@ def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=
     ws = Workspace(B, device)
     d = _lib.Desc()
     d.batch = B
+    d.n_pts = int(n_pts)
     d.eps, d.max_iters, d.sweeps, d.rho_rel, d.alpha = float(eps), int(max_iters), int(sweeps), float(rho_rel), float(alpha)
     d.sigma = float(sigma)
     d.anderson = 0 if anderson else -1

@@ -795,9 +795,10 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     Opts o;
     const double eps = d->eps > 0 ? d->eps : 1e-9;
     o.eps2 = eps * eps;
-    o.alpha = d->alpha > 0 ? d->alpha : 1.3;
-    o.rho_rel = d->rho_rel > 0 ? d->rho_rel : 0.01;
-    o.sigma = d->sigma > 0 ? d->sigma : 1.5;
+    o.alpha = d->alpha;
+    o.rho_rel = d->rho_rel;
+    o.sigma = d->sigma;
+    cvx::default_params(d->n_pts, o.rho_rel, o.alpha, o.sigma);
     o.anderson = d->anderson >= 0;
     o.aa_on2 = cvx::AA_RES2_ON;
     o.rowk = (d->variant == 1) ? 0.0 : 1.0;

@@ -19,11 +19,12 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
 {
     cvx::Opts o;
     o.eps2 = eps * eps;
-    o.alpha = alpha > 0 ? alpha : 1.3;
-    o.rho_rel = rho_rel > 0 ? rho_rel : 0.01;
+    o.alpha = alpha;
+    o.rho_rel = rho_rel;
     o.max_iters = max_iters > 0 ? max_iters : 2500;
     o.sweeps = sweeps > 0 ? sweeps : 1;
-    o.sigma = sigma > 0 ? sigma : 1.5;
+    o.sigma = sigma;
+    cvx::default_params(n_pts, o.rho_rel, o.alpha, o.sigma);
     o.anderson = anderson != 0;
     o.rowk = variant == 1 ? 0.0 : 1.0;
     o.kappa = cvx::DUAL_GUESS;
