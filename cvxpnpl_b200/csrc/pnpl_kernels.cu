@@ -385,18 +385,21 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
         if (lane < cvx::AA_GRAM_WORDS) S.gram[lane] = 0.f;
         if (lane < 16) S.dots[lane] = 0.f;
         int it = (int)h[cvx::HO_IT];
+        double rho = h[cvx::HO_RHO];
         __syncwarp();
         bool converged = false;
-        cvx::warp_dr_loop(S, o, lane, it, converged);
+        cvx::warp_dr_loop(S, o, lane, it, converged, rho);
         for (int p = lane; p < 55; p += 32) {
             int r, c;
             cvx::unpack_idx(p, r, c);
             h[cvx::HO_M + p] = S.M[r * 10 + c];
+            if (r < 9) h[cvx::HO_Q + p] = S.Q[r * 10 + c];   // Q / rho changes with a penalty rescale
         }
         for (int e = lane; e < 100; e += 32) h[cvx::HO_V + e] = S.V[e];
         if (lane < 10) h[cvx::HO_L + lane] = S.L[lane];
         if (lane == 0) {
             h[cvx::HO_IT] = (double)it;
+            h[cvx::HO_RHO] = rho;
             h[cvx::HO_FLAGS] = converged ? 1.0 : 0.0;
         }
         __syncwarp();
@@ -912,8 +915,10 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         const int64_t want32 = (d->batch + NT32 - 1) / NT32;
         const int64_t blocks32 = want32 < slots / NT ? want32 : slots / NT;
         mark(tm, 1, st);
+        // the FP32 phase stops before the penalty rescale of slow problems (RESCALE_AT) is due
+        const int cap32 = d->fp32_iters < cvx::RESCALE_AT ? d->fp32_iters : cvx::RESCALE_AT - 1;
         admm32_kernel<<<(unsigned)blocks32, NT32, SMEM32_BYTES, st>>>(dd, o, ctrl, pre, warm, qr32, blocks32 * NT32,
-                                                                      d->fp32_iters);
+                                                                      cap32);
         mark(tm, 2, st);
         ortho_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, st>>>(d->batch, warm);
         warm_in = warm;

@@ -36,6 +36,17 @@ CVX_HD void default_params(int n_pts, double& rho_rel, double& alpha, double& si
     if (!(alpha > 0)) alpha = 1.5;
 }
 
+// Slow problems get a smaller penalty, once.  A problem still iterating after RESCALE_AT
+// iterations continues with rho <- RESCALE_RHO rho: the scaled dual U = Y / rho grows by
+// 1 / RESCALE_RHO, i.e. in the eigenbasis of M = Z - U the negative eigenvalues are
+// divided by RESCALE_RHO, and so is Q / rho.  Same SDP, same fixed point; measured on
+// seeded batches (mean iterations / problems at the 2500 cap): PnL-6 106 / 19 -> 95 / 5 of
+// 6000, 4 points 356 / 331 -> 262 / 165, PnP-8 max 696 -> 443; well-posed problems never get
+// this far (PnPL 8+4: p99.9 = 107).  Slow problems are the ones whose optimal face is nearly
+// flat (two small eigenvalues of Q); there a smaller rho lets the objective pull harder.
+constexpr int RESCALE_AT = 150;
+constexpr double RESCALE_RHO = 0.35;
+
 struct Problem {
     const double* K;
     const double* pts_2d;
@@ -81,6 +92,31 @@ struct LaneState {
     bool finite, iterating, converged;
     AAState aa;
 };
+
+template <int S, class QRT>
+CVX_HD void rescale_rho(Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
+{
+    const double ic = 1.0 / RESCALE_RHO;
+#pragma unroll 1
+    for (int j = 0; j < 10; ++j) {
+        const double l = L[j];
+        if (!(l < 0.0)) continue;
+        const double dl = l * ic - l;
+#pragma unroll 1
+        for (int r = 0; r < 10; ++r) {
+            const double a = dl * V[r * 10 + j];
+#pragma unroll 1
+            for (int c = 0; c <= r; ++c) M[sidx(r, c)] = fma(a, V[c * 10 + j], M[sidx(r, c)]);
+        }
+        L[j] = l * ic;
+    }
+#pragma unroll 1
+    for (int e = 0; e < 45; ++e) QR[e] = QR[e] * ic;
+    st.rho *= RESCALE_RHO;
+    aa_reset(st.aa);
+    st.res_prev = 1e300;
+}
+
 
 // Assembly for one problem into 46 doubles: Q/rho (45, packed) and rho.  Run by a
 // lane-parallel pre-pass kernel (pre_kernel) so that the persistent solver's
@@ -408,7 +444,10 @@ CVX_HD bool pass_eig(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT 
         L[j] = l;
         dg = fma(l, l, dg);
     }
-    if (st.iterating) return false;
+    if (st.iterating) {
+        if (st.it == RESCALE_AT) rescale_rho(V, M, L, QR, st);
+        return false;
+    }
     if (!isfinite(dg)) return true;  // NaN-safe: a non-finite iterate ends the problem
     if (off > 1e-22 * dg) return false;
     if (st.phase == 2) return true;

@@ -201,7 +201,8 @@ __device__ __forceinline__ bool aa_solve_packed(const float* gram, const float* 
 
 // DR iterations of one problem by one warp.  S holds M, V, L, Q (= Q/rho, full form
 // with a zero last row/column); `it` continues the problem's iteration count.
-__device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, int& it, bool& converged)
+__device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, int& it, bool& converged,
+                                          double& rho)
 {
     const unsigned FULL = 0xffffffffu;
     const double isig = 1.0 / o.sigma, inrm9 = 1.0 / (2.0 + isig * isig);
@@ -446,6 +447,29 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
         }
         if (lane < 10) S.L[lane] = S.T[lane * 11];
         __syncwarp();
+        // ---- 7. slow problem: continue with a smaller penalty, once (rescale_rho) ---------
+        if (it == RESCALE_AT) {
+            const double ic = 1.0 / RESCALE_RHO;
+            _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+                const int r = er[q], c = ec[q];
+                double m = S.M[r * 10 + c];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    const double l = S.L[j];
+                    m = fma((l < 0.0 ? l * ic - l : 0.0) * S.V[r * 10 + j], S.V[c * 10 + j], m);
+                }
+                S.M[r * 10 + c] = m;
+                S.M[c * 10 + r] = m;
+            }
+            for (int e = lane; e < 100; e += 32) S.Q[e] *= ic;
+            __syncwarp();
+            if (lane < 10 && S.L[lane] < 0.0) S.L[lane] *= ic;
+            rho *= RESCALE_RHO;
+            mask = 0u;
+            have_prev = false;
+            res_prev = 1e300;
+            __syncwarp();
+        }
     }
     __syncwarp();
 }

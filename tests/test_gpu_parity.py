@@ -329,7 +329,9 @@ def test_batched_synth_suite(cb):
     cell = suite.run_cell("pnpl", 8, 1.0, 4000, seed=2)
     assert cell.ang_median_deg < 2.0 and cell.failed < 0.01
     cell = suite.run_cell("pnl", 4, 0.0, 2000, seed=3)          # minimal-ish: several candidates
-    assert cell.multi > 0.05 and cell.ang_median_deg < 1e-3
+    # (the share of multi-candidate results shrinks as convergence improves: most rank-2 results
+    # of 4-line problems are iterates that stopped at the cap)
+    assert cell.multi > 0.01 and cell.ang_median_deg < 1e-3
 
 
 def test_rc_variant(cb, golden):
