@@ -37,15 +37,17 @@ CVX_HD void default_params(int n_pts, double& rho_rel, double& alpha, double& si
 }
 
 // Slow problems get a smaller penalty, once.  A problem still iterating after RESCALE_AT
-// iterations continues with rho <- RESCALE_RHO rho: the scaled dual U = Y / rho grows by
-// 1 / RESCALE_RHO, i.e. in the eigenbasis of M = Z - U the negative eigenvalues are
-// divided by RESCALE_RHO, and so is Q / rho.  Same SDP, same fixed point; measured on
+// iterations continues with rho <- 0.35 rho: the scaled dual U = Y / rho grows by
+// 1 / 0.35, i.e. in the eigenbasis of M = Z - U the negative eigenvalues are
+// divided by 0.35, and so is Q / rho.  Same SDP, same fixed point; measured on
 // seeded batches (mean iterations / problems at the 2500 cap): PnL-6 106 / 19 -> 95 / 5 of
 // 6000, 4 points 356 / 331 -> 262 / 165, PnP-8 max 696 -> 443; well-posed problems never get
 // this far (PnPL 8+4: p99.9 = 107).  Slow problems are the ones whose optimal face is nearly
 // flat (two small eigenvalues of Q); there a smaller rho lets the objective pull harder.
+// Problems that are still not done at 400 and at 800 iterations get another factor 0.5 each
+// (PnL-6: 30 -> 7 of 20000 at the cap; 4 points: 121 -> 64 of 3000).
 constexpr int RESCALE_AT = 150;
-constexpr double RESCALE_RHO = 0.35;
+CVX_HD double rescale_factor(int it) { return it == RESCALE_AT ? 0.35 : ((it == 400 || it == 800) ? 0.5 : 0.0); }
 
 struct Problem {
     const double* K;
@@ -94,9 +96,9 @@ struct LaneState {
 };
 
 template <int S, class QRT>
-CVX_HD void rescale_rho(Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
+CVX_HD void rescale_rho(Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st, double factor)
 {
-    const double ic = 1.0 / RESCALE_RHO;
+    const double ic = 1.0 / factor;
 #pragma unroll 1
     for (int j = 0; j < 10; ++j) {
         const double l = L[j];
@@ -112,7 +114,7 @@ CVX_HD void rescale_rho(Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st)
     }
 #pragma unroll 1
     for (int e = 0; e < 45; ++e) QR[e] = QR[e] * ic;
-    st.rho *= RESCALE_RHO;
+    st.rho *= factor;
     aa_reset(st.aa);
     st.res_prev = 1e300;
 }
@@ -445,7 +447,8 @@ CVX_HD bool pass_eig(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT 
         dg = fma(l, l, dg);
     }
     if (st.iterating) {
-        if (st.it == RESCALE_AT) rescale_rho(V, M, L, QR, st);
+        const double rf = rescale_factor(st.it);
+        if (rf > 0.0) rescale_rho(V, M, L, QR, st, rf);
         return false;
     }
     if (!isfinite(dg)) return true;  // NaN-safe: a non-finite iterate ends the problem

@@ -448,8 +448,9 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
         if (lane < 10) S.L[lane] = S.T[lane * 11];
         __syncwarp();
         // ---- 7. slow problem: continue with a smaller penalty, once (rescale_rho) ---------
-        if (it == RESCALE_AT) {
-            const double ic = 1.0 / RESCALE_RHO;
+        const double rf = rescale_factor(it);
+        if (rf > 0.0) {
+            const double ic = 1.0 / rf;
             _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
                 const int r = er[q], c = ec[q];
                 double m = S.M[r * 10 + c];
@@ -464,7 +465,7 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
             for (int e = lane; e < 100; e += 32) S.Q[e] *= ic;
             __syncwarp();
             if (lane < 10 && S.L[lane] < 0.0) S.L[lane] *= ic;
-            rho *= RESCALE_RHO;
+            rho *= rf;
             mask = 0u;
             have_prev = false;
             res_prev = 1e300;
