@@ -929,6 +929,7 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     int64_t wblocks = (blocks * NT + warps_per_cta - 1) / warps_per_cta;   // at most one hand-over per lane
     const int64_t wcap = (slots / NT) * 2;
     if (wblocks > wcap) wblocks = wcap;
+    // (two or three problems per warp were measured too: no difference)
     const int handoff_max = (int)(wblocks * warps_per_cta);
     mark(tm, 3, st);
     solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm_in, grace,
