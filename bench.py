@@ -333,14 +333,18 @@ def run_ours(a):
         value = total / (ms_dev * 1e-3)
         e2e = total / (ms_e2e * 1e-3)
         bpp = BYTES_PER_PROBLEM.get((n_pts, n_lines), 8 * (5 * n_pts + 10 * n_lines) + 96)
+        kind = "PnPL" if (n_pts and n_lines) else ("PnP" if n_pts else "PnL")
+        cfg_name = {(8, 4): "BASELINE.json configs[2]", (8, 0): "BASELINE.json configs[1]",
+                    (0, 6): "BASELINE.json configs[3]"}.get((n_pts, n_lines), "not a BASELINE.json config")
         achieved = bpp * B / (kernel_ms[dominant] * 1e-3) / 1e9
         flops = kc.get("fp64_flops_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if a.admm == "f64" else "f32 first phase + f64 tail/extraction", "data": "synthetic",
-            "config": {"workload": f"{B} x PnPL ({n_pts} pts + {n_lines} lines) per GPU, fp64, sigma={a.noise}px, "
-                                   f"Kinect K (BASELINE.json configs[2])",
+            "config": {"workload": f"{B} x {kind} ({n_pts} pts + {n_lines} lines) per GPU, "
+                                   f"{'fp64' if a.admm == 'f64' else 'fp32 ADMM first phase + fp64'}, sigma={a.noise}px, "
+                                   f"Kinect K ({cfg_name})",
                        "problems_per_gpu_per_step": B, "eps": 1e-9, "max_iters": 2500,
                        "l2": "flushed between timed iterations (256 MB write)",
                        "collective": "all_gather of [B,15] pose records (NCCL)" if world > 1 else "none"},
