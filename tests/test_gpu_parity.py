@@ -451,3 +451,26 @@ def test_fp32_admm_matches_oracle(cb, n_pts, n_lines):
         assert np.linalg.norm(to - tm[i]) / np.linalg.norm(to) <= T_TOL
         checked += 1
     assert checked == 6
+
+
+def test_kernel_times_and_launch_count(cb):
+    """cvxpnpl_b200_kernel_times: CUDA-event time of every kernel of a timed solve; the
+    five (seven) launches of the path are all there and add up to the step."""
+    from cvxpnpl_b200 import synth
+    d = synth.make_batch(20000, 8, 4, noise=1.0, seed=5)
+    for admm, n_launch, extra in (("f64", 5, ()), ("f32", 7, ("admm32_kernel", "ortho_kernel"))):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _solve(cb, d, 8, 4, admm_dtype=admm)        # warm-up
+        s.record()
+        res = _solve(cb, d, 8, 4, admm_dtype=admm, timing=True)
+        e.record()
+        torch.cuda.synchronize()
+        assert res.launches == n_launch
+        t = cb.last_kernel_times()
+        for k in ("pre_kernel", "solve_fused_kernel", "straggler_kernel", "solve_fused_kernel<resume>",
+                  "finish_kernel") + extra:
+            assert t[k] > 0.0, (k, t)
+        if admm == "f64":
+            assert t["admm32_kernel"] == 0.0 and t["ortho_kernel"] == 0.0
+        assert max(t, key=t.get) == "solve_fused_kernel"
+        assert sum(t.values()) <= s.elapsed_time(e) * 1.05
