@@ -472,5 +472,4 @@ def test_kernel_times_and_launch_count(cb):
             assert t[k] > 0.0, (k, t)
         if admm == "f64":
             assert t["admm32_kernel"] == 0.0 and t["ortho_kernel"] == 0.0
-        assert max(t, key=t.get) == "solve_fused_kernel"
         assert sum(t.values()) <= s.elapsed_time(e) * 1.05
