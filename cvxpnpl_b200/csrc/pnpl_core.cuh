@@ -455,7 +455,7 @@ CVX_HD void aa_ld_cols(const Hist& H, int off, int c, uint32_t w[28])
 // res2 is the squared DR residual of the iterate (sets the FP16 scale).  On entry M
 // holds M_k + g_k and G holds g_k (G[55] is a dedicated zero so whole 8-entry chunks
 // can be processed without a bounds test); on exit (active lanes) M holds M_{k+1}.
-// The least squares runs on FP32 sums with an FP64 Cholesky factorisation.  The
+// The least squares runs on FP32 sums with an FP32 Cholesky factorisation.  The
 // Gram matrix is kept across steps; only the row of the new column is recomputed.
 template <int S, class RT, class Hist>
 CVX_HD void aa_step(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bool active, int wslot, float res2)
@@ -534,61 +534,63 @@ CVX_HD void aa_step(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bo
 #pragma unroll
     for (int j = 0; j < AA_M; ++j)
         if (j == wslot) rg[j] = ndg;
-    // normal equations (FP64 Cholesky); columns that are not valid are cut out
-    double A[AA_GRAM_WORDS], r[AA_M];
-    double tr = 0.0;
+    // normal equations (FP32 Cholesky: the Gram matrix is made of FP32 sums anyway, and
+    // measured iteration counts are the same as with an FP64 factorisation); columns that are
+    // not valid are cut out
+    float A[AA_GRAM_WORDS], r[AA_M];
+    float tr = 0.f;
 #pragma unroll
     for (int i = 0; i < AA_M; ++i) {
         const bool vi = (aa.mask >> i) & 1u;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
             const bool vj = (aa.mask >> j) & 1u;
-            A[(i * (i + 1)) / 2 + j] = (vi && vj) ? (double)gram[(i * (i + 1)) / 2 + j] : 0.0;
+            A[(i * (i + 1)) / 2 + j] = (vi && vj) ? gram[(i * (i + 1)) / 2 + j] : 0.f;
         }
-        r[i] = vi ? (double)rg[i] : 0.0;
+        r[i] = vi ? rg[i] : 0.f;
         tr += A[(i * (i + 1)) / 2 + i];
     }
-    bool pd = tr > 0.0;
+    bool pd = tr > 0.f;
 #pragma unroll
-    for (int i = 0; i < AA_M; ++i) A[(i * (i + 1)) / 2 + i] += 1e-7 * tr + (((aa.mask >> i) & 1u) ? 0.0 : 1.0);
+    for (int i = 0; i < AA_M; ++i) A[(i * (i + 1)) / 2 + i] += 1e-6f * tr + (((aa.mask >> i) & 1u) ? 0.f : 1.f);
     // A = L L' in place (L[i][i] holds the RECIPROCAL pivot), then two triangular solves.
     // All loops have constant bounds with guards, so they unroll completely and A, r
     // stay in registers.
 #define CVX_TI(i, j) (((i) * ((i) + 1)) / 2 + (j))
 #pragma unroll
     for (int j = 0; j < AA_M; ++j) {
-        double d = A[CVX_TI(j, j)];
+        float d = A[CVX_TI(j, j)];
 #pragma unroll
         for (int k = 0; k < AA_M; ++k)
-            if (k < j) d = fma(-A[CVX_TI(j, k)], A[CVX_TI(j, k)], d);
-        pd = pd && (d > 0.0);
-        const double id = cvx_rsqrt(pd ? d : 1.0);
+            if (k < j) d = fmaf(-A[CVX_TI(j, k)], A[CVX_TI(j, k)], d);
+        pd = pd && (d > 0.f);
+        const float id = f32::cvx_rsqrt(pd ? d : 1.f);
         A[CVX_TI(j, j)] = id;
 #pragma unroll
         for (int i = 0; i < AA_M; ++i) {
             if (i <= j) continue;
-            double t = A[CVX_TI(i, j)];
+            float t = A[CVX_TI(i, j)];
 #pragma unroll
             for (int k = 0; k < AA_M; ++k)
-                if (k < j) t = fma(-A[CVX_TI(i, k)], A[CVX_TI(j, k)], t);
+                if (k < j) t = fmaf(-A[CVX_TI(i, k)], A[CVX_TI(j, k)], t);
             A[CVX_TI(i, j)] = t * id;
         }
     }
 #pragma unroll
     for (int i = 0; i < AA_M; ++i) {
-        double t = r[i];
+        float t = r[i];
 #pragma unroll
         for (int k = 0; k < AA_M; ++k)
-            if (k < i) t = fma(-A[CVX_TI(i, k)], r[k], t);
+            if (k < i) t = fmaf(-A[CVX_TI(i, k)], r[k], t);
         r[i] = t * A[CVX_TI(i, i)];
     }
 #pragma unroll
     for (int ii = 0; ii < AA_M; ++ii) {
         const int i = AA_M - 1 - ii;
-        double t = r[i];
+        float t = r[i];
 #pragma unroll
         for (int k = 0; k < AA_M; ++k)
-            if (k > i) t = fma(-A[CVX_TI(k, i)], r[k], t);
+            if (k > i) t = fmaf(-A[CVX_TI(k, i)], r[k], t);
         r[i] = t * A[CVX_TI(i, i)];
     }
 #undef CVX_TI
@@ -597,7 +599,7 @@ CVX_HD void aa_step(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bo
 #pragma unroll
     for (int j = 0; j < AA_M; ++j) ok = ok && isfinite(r[j]);
 #pragma unroll
-    for (int j = 0; j < AA_M; ++j) f[j] = (ok && ((aa.mask >> j) & 1u)) ? (float)r[j] : 0.f;
+    for (int j = 0; j < AA_M; ++j) f[j] = (ok && ((aa.mask >> j) & 1u)) ? r[j] : 0.f;
     H.wait_st();
 
     // ---- B. extrapolate optimistically: M -= sum_j gamma_j (dM_j + dG_j); remember g_k

@@ -140,54 +140,54 @@ __device__ __forceinline__ void round_pair(int r, int k, int& p, int& q)
 __device__ __forceinline__ bool aa_solve_packed(const float* gram, const float* rg, uint32_t mask, float f[AA_M])
 {
 #define CVX_TI(i, j) (((i) * ((i) + 1)) / 2 + (j))
-    double A[AA_GRAM_WORDS], r[AA_M];
-    double tr = 0.0;
+    float A[AA_GRAM_WORDS], r[AA_M];
+    float tr = 0.f;
 #pragma unroll
     for (int i = 0; i < AA_M; ++i) {
         const bool vi = (mask >> i) & 1u;
 #pragma unroll
         for (int j = 0; j < AA_M; ++j)
-            if (j <= i) A[CVX_TI(i, j)] = (vi && ((mask >> j) & 1u)) ? (double)gram[CVX_TI(i, j)] : 0.0;
-        r[i] = vi ? (double)rg[i] : 0.0;
+            if (j <= i) A[CVX_TI(i, j)] = (vi && ((mask >> j) & 1u)) ? gram[CVX_TI(i, j)] : 0.f;
+        r[i] = vi ? rg[i] : 0.f;
         tr += A[CVX_TI(i, i)];
     }
-    bool pd = tr > 0.0;
+    bool pd = tr > 0.f;
 #pragma unroll
-    for (int i = 0; i < AA_M; ++i) A[CVX_TI(i, i)] += 1e-7 * tr + (((mask >> i) & 1u) ? 0.0 : 1.0);
+    for (int i = 0; i < AA_M; ++i) A[CVX_TI(i, i)] += 1e-6f * tr + (((mask >> i) & 1u) ? 0.f : 1.f);
 #pragma unroll
     for (int j = 0; j < AA_M; ++j) {
-        double d = A[CVX_TI(j, j)];
+        float d = A[CVX_TI(j, j)];
 #pragma unroll
         for (int k = 0; k < AA_M; ++k)
-            if (k < j) d = fma(-A[CVX_TI(j, k)], A[CVX_TI(j, k)], d);
-        pd = pd && (d > 0.0);
-        const double id = rsqrt(pd ? d : 1.0);
+            if (k < j) d = fmaf(-A[CVX_TI(j, k)], A[CVX_TI(j, k)], d);
+        pd = pd && (d > 0.f);
+        const float id = rsqrtf(pd ? d : 1.f);
         A[CVX_TI(j, j)] = id;
 #pragma unroll
         for (int i = 0; i < AA_M; ++i) {
             if (i <= j) continue;
-            double t = A[CVX_TI(i, j)];
+            float t = A[CVX_TI(i, j)];
 #pragma unroll
             for (int k = 0; k < AA_M; ++k)
-                if (k < j) t = fma(-A[CVX_TI(i, k)], A[CVX_TI(j, k)], t);
+                if (k < j) t = fmaf(-A[CVX_TI(i, k)], A[CVX_TI(j, k)], t);
             A[CVX_TI(i, j)] = t * id;
         }
     }
 #pragma unroll
     for (int i = 0; i < AA_M; ++i) {
-        double t = r[i];
+        float t = r[i];
 #pragma unroll
         for (int k = 0; k < AA_M; ++k)
-            if (k < i) t = fma(-A[CVX_TI(i, k)], r[k], t);
+            if (k < i) t = fmaf(-A[CVX_TI(i, k)], r[k], t);
         r[i] = t * A[CVX_TI(i, i)];
     }
 #pragma unroll
     for (int ii = 0; ii < AA_M; ++ii) {
         const int i = AA_M - 1 - ii;
-        double t = r[i];
+        float t = r[i];
 #pragma unroll
         for (int k = 0; k < AA_M; ++k)
-            if (k > i) t = fma(-A[CVX_TI(k, i)], r[k], t);
+            if (k > i) t = fmaf(-A[CVX_TI(k, i)], r[k], t);
         r[i] = t * A[CVX_TI(i, i)];
     }
 #undef CVX_TI
@@ -195,7 +195,7 @@ __device__ __forceinline__ bool aa_solve_packed(const float* gram, const float* 
 #pragma unroll
     for (int j = 0; j < AA_M; ++j) ok = ok && isfinite(r[j]);
 #pragma unroll
-    for (int j = 0; j < AA_M; ++j) f[j] = (ok && ((mask >> j) & 1u)) ? (float)r[j] : 0.f;
+    for (int j = 0; j < AA_M; ++j) f[j] = (ok && ((mask >> j) & 1u)) ? r[j] : 0.f;
     return ok;
 }
 
