@@ -815,7 +815,7 @@ constexpr int64_t WS_HEADER_DOUBLES = 16;
 
 // thread slots of the persistent grid: one CTA of NT threads per SM.  Without a
 // CUDA device (CPU-side callers sizing buffers) a generous 256 SMs is assumed.
-int64_t device_slots()
+int64_t device_slots_all()
 {
     int dev = 0, n_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -824,6 +824,16 @@ int64_t device_slots()
         n_sm = 256;
     }
     return (int64_t)n_sm * NT;
+}
+
+// thread slots a batch actually uses: whole CTAs, never more than one per SM (small batches
+// -- the scalar drop-in API solves one problem per call -- then need a small workspace)
+int64_t device_slots_all();
+int64_t device_slots(int64_t batch)
+{
+    const int64_t all = device_slots_all();
+    const int64_t want = ((batch + NT - 1) / NT) * NT;
+    return want < all ? (want > 0 ? want : NT) : all;
 }
 
 // workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | parked results 112 x batch doubles |
@@ -851,7 +861,7 @@ int cvxpnpl_b200_last_launch_count(void) { return g_launches; }
 size_t cvxpnpl_b200_workspace_bytes(int64_t batch)
 {
     if (batch <= 0) return 0;
-    return ws_bytes_for(device_slots(), batch);
+    return ws_bytes_for(device_slots(batch), batch);
 }
 
 int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
@@ -884,7 +894,7 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int64_t slots = device_slots();
+    const int64_t slots = device_slots(d->batch);
     // persistent grid: one CTA per SM (shared memory allows exactly one), never more
     // CTAs than there is work for
     const int64_t want = (d->batch + NT - 1) / NT;
@@ -897,7 +907,10 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     double* pre = park + d->batch * cvx::PARK_DOUBLES;
     double* slab = pre + d->batch * cvx::PRE_DOUBLES;
     // hand-over grace (passes after the queue ran dry); desc.handoff: 0 default, < 0 never
-    const int grace = d->handoff < 0 ? -1 : (d->handoff > 0 ? d->handoff : 40);
+    // (a batch that fits the straggler grid -- one warp per problem -- goes there at once: for
+    // the scalar API that is 0.2 ms instead of 1.1 ms per call)
+    const int64_t n_sm = device_slots_all() / NT;
+    const int grace = d->handoff < 0 ? -1 : (d->handoff > 0 ? d->handoff : (d->batch <= n_sm * 2 * (NT_W / 32) ? 1 : 40));
     const Opts o = make_opts(d);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e0 = cudaMemsetAsync(ctrl, 0, WS_HEADER_DOUBLES * sizeof(double), st);
@@ -927,7 +940,7 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     // straggler grid: one warp per handed-over problem, at most 2 CTAs of 8 warps per SM
     const int64_t warps_per_cta = NT_W / 32;
     int64_t wblocks = (blocks * NT + warps_per_cta - 1) / warps_per_cta;   // at most one hand-over per lane
-    const int64_t wcap = (slots / NT) * 2;
+    const int64_t wcap = n_sm * 2;
     if (wblocks > wcap) wblocks = wcap;
     // (two or three problems per warp were measured too: no difference)
     const int handoff_max = (int)(wblocks * warps_per_cta);
@@ -1050,7 +1063,7 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int64_t slots = device_slots();
+    const int64_t slots = device_slots(d->batch);
     const int64_t want = (d->batch + NT - 1) / NT;
     const int64_t blocks = want < slots / NT ? want : slots / NT;
     cvxpnpl_b200_desc dd = *d;

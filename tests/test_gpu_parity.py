@@ -275,7 +275,8 @@ def test_stage_entry_points_compose(cb):
     Z, dobj, iters, status = cb.solve_sdp_batched(Q)
     res = cb.extract_batched(Z, Q, Bm, dobj)
     torch.cuda.synchronize()
-    assert float((iters - fused.iters).abs().float().mean()) < 3.0   # same algorithm; Anderson rounding differs
+    # same algorithm; the Anderson history differs (a batch this small runs in the warp kernel: FP32 history)
+    assert float((iters - fused.iters).abs().float().mean()) < 6.0
     assert float((res.R[:, 0] - fused.R[:, 0]).abs().max()) < 1e-9
     assert float((res.t[:, 0] - fused.t[:, 0]).abs().max()) < 1e-9
 
