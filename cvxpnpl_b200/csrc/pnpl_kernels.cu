@@ -21,6 +21,7 @@
 namespace {
 
 constexpr int NT = 128;                    // problems (threads) per CTA
+constexpr int N_BUCKETS = 64;              // difficulty buckets of the work queue
 constexpr int SMEM_DOUBLES = 221;          // V 100 + M 55 + T 55 (+1 zero pad) + lambda 10
 constexpr size_t SMEM_BYTES = (size_t)NT * SMEM_DOUBLES * sizeof(double);
 
@@ -187,7 +188,7 @@ enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3
 template <bool RESUME>
 __global__ void __launch_bounds__(NT, 1)
 solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const double* pre, double* park,
-                   double* slab, const double* warm, int grace, int handoff_max, int64_t ws_stride)
+                   double* slab, const double* warm, const int32_t* order, int grace, int handoff_max, int64_t ws_stride)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
@@ -234,7 +235,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
                 if (RESUME) {
                     b = cvx::problem_resume(slab + nb * cvx::HAND_DOUBLES, V, M, L, QR, st);
                 } else {
-                    b = (int64_t)nb;
+                    b = (int64_t)order[nb];   // queue position -> problem (likely stragglers first)
                     if (warm)   // the FP32 first phase has already brought the problem into the tail
                         cvx::problem_begin_warm(pre + b * cvx::PRE_DOUBLES, warm + b * cvx::WARM_DOUBLES, o, V, M, L, QR,
                                                 st);
@@ -297,7 +298,7 @@ constexpr int NT32 = 256;
 constexpr size_t SMEM32_BYTES = (size_t)NT32 * SMEM_DOUBLES * sizeof(float);
 __global__ void __launch_bounds__(NT32, 1)
 admm32_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const double* pre, double* warm, float* qr32,
-              int64_t stride32, int cap32)
+              const int32_t* order, int64_t stride32, int cap32)
 {
     extern __shared__ float smf[];
     const int tid = threadIdx.x;
@@ -315,7 +316,7 @@ admm32_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const doubl
         if (b < 0 && !exhausted) {
             const unsigned long long nb = atomicAdd(ctrl + CTRL_NEXT32, 1ULL);
             if (nb < (unsigned long long)d.batch) {
-                b = (int64_t)nb;
+                b = (int64_t)order[nb];
                 const double* pb = pre + b * cvx::PRE_DOUBLES;
                 cvx::problem_begin32(pb, o, V, M, L, QR);
                 finite = isfinite(pb[45]);
@@ -412,7 +413,35 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
 // ---------------------------------------------------------------------------------
 constexpr int NT_P = 64;
 constexpr size_t SMEM_P_BYTES = (size_t)NT_P * 100 * sizeof(double);   // V (T stays in registers)
-__global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre)
+// Difficulty-ordered work queue.  The slow problems of a batch are the ones whose optimal face
+// is nearly flat: two small eigenvalues of Q (measured on seeded batches: 90 % of the 1 % slowest
+// problems are among the quarter of the batch with the smallest second eigenvalue).  The
+// eigenvalues come for free with the start decomposition, so the pre-pass drops every problem
+// into one of 64 buckets by lambda_2(Q) / ||Q||_F (third-octave steps), a counting sort turns
+// the buckets into a permutation, and the persistent kernel pulls the likely stragglers FIRST:
+// they are then well advanced when the queue runs dry, and the straggler phase is shorter.
+__device__ __forceinline__ int difficulty_bucket(const double* rec, const Opts& o)
+{
+    // eigenvalues of M0 = blkdiag(I/3 - kappa Q/rho, sigma^2): entries 0..8 belong to Q
+    double m1 = -1e300, m2 = -1e300;   // the two largest of 1/3 - kappa lambda_j / rho
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const double l = rec[cvx::PRE_L + j];
+        if (l > m1) {
+            m2 = m1;
+            m1 = l;
+        } else if (l > m2) {
+            m2 = l;
+        }
+    }
+    const double lam2 = (1.0 / 3.0 - m2) / o.kappa * o.rho_rel;   // lambda_2(Q) / ||Q||_F
+    if (!(lam2 > 0.0) || !isfinite(lam2)) return N_BUCKETS - 1;
+    const int k = (int)floor((log2(lam2) + 20.0) * 3.0);
+    return k < 0 ? 0 : (k > N_BUCKETS - 1 ? N_BUCKETS - 1 : k);
+}
+
+__global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre, unsigned* bucket_count,
+                                                   unsigned char* bucket_of)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
@@ -422,6 +451,28 @@ __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, 
     double* out = pre + b * cvx::PRE_DOUBLES;
     cvx::assemble_scaled(problem_at(d, b), o, out);
     cvx::start_decomposition(out, o, V);   // eigen-decomposition of the start point (cold Jacobi)
+    const int k = (o.kappa != 0.0) ? difficulty_bucket(out, o) : 0;
+    bucket_of[b] = (unsigned char)k;
+    atomicAdd(bucket_count + k, 1u);
+}
+
+// counting sort of the buckets -> queue order (likely stragglers first)
+__global__ void bucket_scan_kernel(const unsigned* count, unsigned* offset)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned acc = 0;
+        for (int k = 0; k < N_BUCKETS; ++k) {
+            offset[k] = acc;
+            acc += count[k];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(int64_t batch, const unsigned char* bucket_of,
+                                                             unsigned* offset, int32_t* order)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    order[atomicAdd(offset + bucket_of[b], 1u)] = (int32_t)b;
 }
 
 // ---------------------------------------------------------------------------------
@@ -811,7 +862,8 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     return o;
 }
 
-constexpr int64_t WS_HEADER_DOUBLES = 16;
+// header: 16 control words, then the difficulty buckets of the work queue (64 counts, 64 offsets; unsigned int)
+constexpr int64_t WS_HEADER_DOUBLES = 16 + N_BUCKETS;   // 16 x 8 B + 2 x 64 x 4 B
 
 // thread slots of the persistent grid: one CTA of NT threads per SM.  Without a
 // CUDA device (CPU-side callers sizing buffers) a generous 256 SMs is assumed.
@@ -839,7 +891,8 @@ int64_t device_slots(int64_t batch)
 // workspace layout: [header 16 doubles | Q/rho 45 x slots doubles | parked results 112 x batch doubles |
 //                    pre-pass 46 x batch doubles | hand-over slab 216 x slots doubles |
 //                    AA history AA_WORDS x slots words (stage kernel only; the fused kernel uses TMEM) |
-//                    FP32-phase export 166 x batch doubles | FP32 Q/rho 45 x 2 slots floats]
+//                    FP32-phase export 166 x batch doubles | FP32 Q/rho 45 x 2 slots floats |
+//                    queue order batch x int32 | difficulty bucket batch x byte]
 size_t ws_bytes_for(int64_t slots, int64_t batch)
 {
     return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES) +
@@ -847,7 +900,9 @@ size_t ws_bytes_for(int64_t slots, int64_t batch)
                sizeof(double) +
            (size_t)slots * cvx::AA_WORDS * sizeof(float) +
            // FP32 first phase: exported state per problem, Q/rho scratch of its 2x wider grid
-           (size_t)batch * cvx::WARM_DOUBLES * sizeof(double) + (size_t)slots * 2 * 45 * sizeof(float);
+           (size_t)batch * cvx::WARM_DOUBLES * sizeof(double) + (size_t)slots * 2 * 45 * sizeof(float) +
+           // queue order (int32) and bucket (byte) per problem
+           (((size_t)batch * 5 + 15) / 16) * 16;
 }
 
 }  // namespace
@@ -917,21 +972,28 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
     const bool tm = d->timing != 0;
     g_ev_n = 0;
+    // regions behind the hand-over slab (see ws_bytes_for)
+    double* warm = (double*)((uint32_t*)(slab + slots * cvx::HAND_DOUBLES) + slots * cvx::AA_WORDS);
+    float* qr32 = (float*)(warm + d->batch * cvx::WARM_DOUBLES);
+    int32_t* order = (int32_t*)(qr32 + slots * 2 * 45);
+    unsigned char* bucket_of = (unsigned char*)(order + d->batch);
+    unsigned* bucket_count = (unsigned*)(ctrl + 16);
+    unsigned* bucket_offset = bucket_count + N_BUCKETS;
     mark(tm, 0, st);
-    pre_kernel<<<(unsigned)((d->batch + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(dd, o, pre);
-    g_launches = 3;
+    pre_kernel<<<(unsigned)((d->batch + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(dd, o, pre, bucket_count, bucket_of);
+    bucket_scan_kernel<<<1, 32, 0, st>>>(bucket_count, bucket_offset);
+    bucket_scatter_kernel<<<(unsigned)((d->batch + 255) / 256), 256, 0, st>>>(d->batch, bucket_of, bucket_offset, order);
+    g_launches = 5;
     const double* warm_in = nullptr;
     if (d->fp32_iters > 0) {
         // FP32 first phase, then its bases made orthonormal in FP64
-        double* warm = (double*)((uint32_t*)(slab + slots * cvx::HAND_DOUBLES) + slots * cvx::AA_WORDS);
-        float* qr32 = (float*)(warm + d->batch * cvx::WARM_DOUBLES);
         const int64_t want32 = (d->batch + NT32 - 1) / NT32;
         const int64_t blocks32 = want32 < slots / NT ? want32 : slots / NT;
         mark(tm, 1, st);
         // the FP32 phase stops before the penalty rescale of slow problems (RESCALE_AT) is due
         const int cap32 = d->fp32_iters < cvx::RESCALE_AT ? d->fp32_iters : cvx::RESCALE_AT - 1;
-        admm32_kernel<<<(unsigned)blocks32, NT32, SMEM32_BYTES, st>>>(dd, o, ctrl, pre, warm, qr32, blocks32 * NT32,
-                                                                      cap32);
+        admm32_kernel<<<(unsigned)blocks32, NT32, SMEM32_BYTES, st>>>(dd, o, ctrl, pre, warm, qr32, order,
+                                                                      blocks32 * NT32, cap32);
         mark(tm, 2, st);
         ortho_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, st>>>(d->batch, warm);
         warm_in = warm;
@@ -945,14 +1007,14 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     // (two or three problems per warp were measured too: no difference)
     const int handoff_max = (int)(wblocks * warps_per_cta);
     mark(tm, 3, st);
-    solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm_in, grace,
-                                                                        handoff_max, slots);
+    solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm_in, order,
+                                                                        grace, handoff_max, slots);
     if (grace >= 0) {
         mark(tm, 4, st);
         straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab);
         mark(tm, 5, st);
-        solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, -1, 0,
-                                                                          slots);
+        solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, nullptr,
+                                                                          -1, 0, slots);
         g_launches += 2;
     }
     mark(tm, 6, st);

@@ -409,7 +409,7 @@ def test_straggler_warp_path_matches_thread_path(cb, n_pts, n_lines):
     d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=77)
     a = _solve(cb, d, n_pts, n_lines, handoff=-1)
     w = _solve(cb, d, n_pts, n_lines, handoff=1)
-    assert a.launches == 3 and w.launches == 5
+    assert a.launches == 5 and w.launches == 7   # pre + 2 sort + solver + finish (+ straggler + resume)
     sa, sw = (a.status & 0xFF).cpu().numpy(), (w.status & 0xFF).cpu().numpy()
     ok = (sa == 0) & (sw == 0) & (a.n_poses.cpu().numpy() == 1) & (w.n_poses.cpu().numpy() == 1)
     assert ok.mean() > (0.95 if n_pts + n_lines > 4 else 0.5)
@@ -456,10 +456,10 @@ def test_fp32_admm_matches_oracle(cb, n_pts, n_lines):
 
 def test_kernel_times_and_launch_count(cb):
     """cvxpnpl_b200_kernel_times: CUDA-event time of every kernel of a timed solve; the
-    five (seven) launches of the path are all there and add up to the step."""
+    seven (nine) launches of the path are all there and add up to the step."""
     from cvxpnpl_b200 import synth
     d = synth.make_batch(20000, 8, 4, noise=1.0, seed=5)
-    for admm, n_launch, extra in (("f64", 5, ()), ("f32", 7, ("admm32_kernel", "ortho_kernel"))):
+    for admm, n_launch, extra in (("f64", 7, ()), ("f32", 9, ("admm32_kernel", "ortho_kernel"))):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _solve(cb, d, 8, 4, admm_dtype=admm)        # warm-up
         s.record()
