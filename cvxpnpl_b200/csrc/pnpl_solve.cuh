@@ -126,7 +126,10 @@ CVX_HD void rescale_rho(Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st, dou
 // ... followed by the eigen-decomposition of the start point (V 100, lambda 10): 156 doubles.
 constexpr int PRE_DOUBLES = 156;
 constexpr int PRE_V = 46, PRE_L = 146;
-constexpr double DUAL_GUESS = 0.75;
+#ifndef CVX_DUAL_GUESS
+#define CVX_DUAL_GUESS 0.75
+#endif
+constexpr double DUAL_GUESS = CVX_DUAL_GUESS;
 
 template <class QOut>
 CVX_HD void assemble_scaled(const Problem& pr, const Opts& o, QOut out)
