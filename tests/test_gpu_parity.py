@@ -474,3 +474,22 @@ def test_kernel_times_and_launch_count(cb):
         if admm == "f64":
             assert t["admm32_kernel"] == 0.0 and t["ortho_kernel"] == 0.0
         assert sum(t.values()) <= s.elapsed_time(e) * 1.05
+
+
+def test_host_pipeline_matches_direct_solve(cb):
+    """HostPipeline (double-buffered pinned-host staging) returns the same records as a
+    direct solve of the same batches, in order."""
+    from cvxpnpl_b200 import synth
+    from cvxpnpl_b200.distributed import unpack_record
+    batches = [synth.make_batch(3000, 8, 4, noise=1.0, seed=100 + i) for i in range(3)]
+    hosts = [{k: torch.from_numpy(b[k]).pin_memory() for k in ("pts_2d", "pts_3d", "line_2d", "line_3d")} for b in batches]
+    pipe = cb.HostPipeline(batches[0]["K"], "cuda:0")
+    for i, b in enumerate(batches):
+        rec = pipe.step(hosts[i], hosts[i + 1] if i + 1 < len(hosts) else None)
+        torch.cuda.synchronize()
+        R, t, n, st, it = unpack_record(rec.clone())
+        ref = _solve(cb, b, 8, 4)
+        ok = ((ref.status & 0xFF) == 0).cpu() & ((st & 0xFF) == 0)
+        assert ok.float().mean() > 0.99
+        assert float((R[ok] - ref.R[:, 0].cpu()[ok]).abs().max()) < 1e-7
+        assert float((t[ok] - ref.t[:, 0].cpu()[ok]).abs().max()) < 1e-7
