@@ -925,6 +925,7 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     if (int rc = check_common(d)) return rc;
     if (d->batch == 0) return 0;
     if (d->n_pts + d->n_lines <= 0) return fail(-4, "no correspondences");
+    if (d->batch > 2000000000LL) return fail(-8, "at most 2e9 problems per call (32-bit queue order)");
     if (!d->K || (d->n_pts && (!d->pts_2d || !d->pts_3d)) || (d->n_lines && (!d->line_2d || !d->line_3d)))
         return fail(-5, "null input pointer");
     if (!d->R || !d->t || !d->n_poses || !d->status || !d->iters) return fail(-6, "null output pointer");
