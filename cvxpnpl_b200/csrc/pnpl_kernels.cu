@@ -1,11 +1,16 @@
 // pnpl_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of cvxpnpl_b200.
 //
-// Execution model: one thread per pose problem, 128 problems per CTA, one CTA per
-// SM.  The per-problem state -- eigenbasis V 100, DR iterate M 55, rotated matrix
-// T 55, eigenvalues 10 doubles -- fills 220 KB of the SM's shared memory in a
-// [element][thread] layout; during a Jacobi sweep T lives in registers.  Q/rho
-// (45 doubles per problem, read once per iteration) is parked in an L2-resident
-// scratch.  Nothing but the correspondences (in) and the poses (out) touches HBM.
+// One batched solve = pre-pass (assembly, start decomposition, difficulty bucket) ->
+// counting sort of the work queue -> [FP32 first phase] -> persistent FP64 solver ->
+// warp-per-problem straggler kernel -> resume (polish) -> finish (pose extraction).
+//
+// The persistent solver: one thread per pose problem, 128 problems per CTA, one CTA
+// per SM.  The per-problem state -- eigenbasis V 100, DR iterate M 55, rotated matrix
+// T 55, eigenvalues 10 doubles -- fills 221 KB of the SM's shared memory in a
+// [element][thread] layout; during a Jacobi sweep T lives in registers; the Anderson
+// history lives in tensor memory.  Q/rho (45 doubles per problem, read once per
+// iteration) is parked in an L2-resident scratch.  Besides the correspondences (in) and
+// the poses (out), only the small per-problem records that connect the kernels touch HBM.
 // See DESIGN.md for the layout and the roofline discussion.
 #include <cuda_runtime.h>
 
@@ -291,7 +296,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
 // FP32 first phase (desc.fp32_iters > 0; BASELINE.json configs[3]).  Same persistent,
 // work-stealing structure as the FP64 solver, but the per-problem state is 221 floats:
 // 256 problems per CTA, two warps per scheduler.  A problem leaves when its DR residual
-// is below the threshold from which the FP64 solver accelerates (||X - Z||_F < 0.05),
+// is below the threshold from which the FP64 solver accelerates (||X - Z||_F < 0.15),
 // or at the FP32 iteration cap.  No Anderson steps, no tensor memory.
 // ---------------------------------------------------------------------------------
 constexpr int NT32 = 256;

@@ -120,7 +120,7 @@ CVX_HD void rescale_rho(Arr<S> V, Arr<S> M, Arr<S> L, QRT QR, LaneState& st, dou
 }
 
 
-// Assembly for one problem into 46 doubles: Q/rho (45, packed) and rho.  Run by a
+// Assembly for one problem into the first 46 doubles of its record: Q/rho (45, packed) and rho.  Run by a
 // lane-parallel pre-pass kernel (pre_kernel) so that the persistent solver's
 // problem_begin -- which executes with a single active lane -- only has to copy.
 // ... followed by the eigen-decomposition of the start point (V 100, lambda 10): 156 doubles.
@@ -252,7 +252,7 @@ CVX_HD void problem_begin(const double* pre, const Opts& o, Arr<S> V, Arr<S> M, 
 // FP32 first phase (BASELINE.json configs[3]: "fp32 ADMM + fp64 extraction").  The
 // DR iteration is self-correcting -- any M is a valid state -- so the iterations that
 // only have to bring a problem from the cold start into the linear tail (||X - Z||_F
-// from ~50 down to 0.05, about 45 of the ~70 iterations, no Anderson steps yet) can run
+// from ~50 down to 0.15, about 25 of the ~55 iterations, no Anderson steps yet) can run
 // in FP32: twice the FMA rate, half the shared memory per problem (so 256 instead of
 // 128 problems per SM and two warps per scheduler instead of one).  The FP32 kernel
 // exports (M, V, lambda, iteration count) per problem as doubles (WARM_DOUBLES); V is
