@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(int64_t batch, cons
 // lane-parallel (re-assembly, rank test, rank-1 / multi-solution recovery, SVD
 // projection, translation, optimality flag, optional Z).
 // ---------------------------------------------------------------------------------
-constexpr int NT_F = 64;
+constexpr int NT_F = 32;
 constexpr size_t SMEM_F_BYTES = (size_t)NT_F * 172 * sizeof(double);   // V 100 + Q 45 + B 27
 __global__ void __launch_bounds__(NT_F) finish_kernel(cvxpnpl_b200_desc d, Opts o, const double* park)
 {

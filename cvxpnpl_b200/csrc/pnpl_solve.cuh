@@ -186,7 +186,7 @@ CVX_HD void start_decomposition(double* pre, const Opts& o, Arr<S> V)
             double dg = 0;
 #pragma unroll
             for (int j = 0; j < 10; ++j) dg = fma(t[sidx(j, j)], t[sidx(j, j)], dg);
-            if (!(jacobi_sweep_reg(t, V) > 1e-14 * dg)) break;
+            if (!(jacobi_sweep_reg(t, V) > 1e-10 * dg)) break;
         }
     }
 #pragma unroll 4
