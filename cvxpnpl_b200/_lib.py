@@ -48,6 +48,8 @@ class Desc(ctypes.Structure):
         ("workspace_bytes", ctypes.c_size_t),
         ("fp32_iters", ctypes.c_int32),
         ("timing", ctypes.c_int32),
+        ("skip_prepass", ctypes.c_int32),
+        ("reserved3", ctypes.c_int32),
     ]
 
 
@@ -63,6 +65,7 @@ EXPORTS = (
     "cvxpnpl_b200_fp64_probe",
     "cvxpnpl_b200_null",
     "cvxpnpl_b200_kernel_times",
+    "cvxpnpl_b200_prepass",
 )
 
 _lib = None
@@ -98,6 +101,8 @@ def load():
                                          ctypes.c_void_p, ctypes.c_void_p]
     lib.cvxpnpl_b200_null.restype = ctypes.c_int
     lib.cvxpnpl_b200_null.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p]
+    lib.cvxpnpl_b200_prepass.restype = ctypes.c_int
+    lib.cvxpnpl_b200_prepass.argtypes = [ctypes.POINTER(Desc), ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
     lib.cvxpnpl_b200_kernel_times.restype = ctypes.c_int
     lib.cvxpnpl_b200_kernel_times.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.cvxpnpl_b200_last_launch_count.restype = ctypes.c_int

@@ -64,7 +64,7 @@ class Workspace:
 def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1e-9, max_iters=2500,
                   sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, variant="full", return_Z=False, return_obj=True, workspace=None,
                   out: Optional[BatchedPoses] = None, device=None, handoff=0, admm_dtype="f64",
-                  fp32_iters=400, timing=False) -> BatchedPoses:
+                  fp32_iters=400, timing=False, _prepass_hook=None) -> BatchedPoses:
     """Solve B problems.  pts_2d [B,n,2], pts_3d [B,n,3], line_2d [B,m,2,2],
     line_3d [B,m,2,3], K [3,3] or [B,3,3]; any of the point / line pairs may be
     omitted (PnP / PnL / PnPL: cvxpnpl.py:523-627).  variant="rc" solves the ablation
@@ -165,8 +165,13 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
         d.workspace, d.workspace_bytes = _ptr(workspace.buf), workspace.nbytes
         stream = torch.cuda.current_stream(device).cuda_stream
+        extra = 0
+        if _prepass_hook is not None:
+            # the caller streams the inputs in and runs the pre-pass chunk by chunk (pipeline.solve_from_host)
+            extra = _prepass_hook(lib, d, stream)
+            d.skip_prepass = 1
         _lib.check(lib.cvxpnpl_b200_solve(ctypes.byref(d), ctypes.c_void_p(stream)))
-        out.launches = int(lib.cvxpnpl_b200_last_launch_count())
+        out.launches = int(lib.cvxpnpl_b200_last_launch_count()) + extra
     return out
 
 

@@ -446,12 +446,12 @@ __device__ __forceinline__ int difficulty_bucket(const double* rec, const Opts& 
 }
 
 __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre, unsigned* bucket_count,
-                                                   unsigned char* bucket_of)
+                                                   unsigned char* bucket_of, int64_t first, int64_t last)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
-    const int64_t b = (int64_t)blockIdx.x * NT_P + tid;
-    if (b >= d.batch) return;
+    const int64_t b = first + (int64_t)blockIdx.x * NT_P + tid;
+    if (b >= last) return;
     cvx::Arr<NT_P> V{smem + tid};
     double* out = pre + b * cvx::PRE_DOUBLES;
     cvx::assemble_scaled(problem_at(d, b), o, out);
@@ -924,7 +924,9 @@ size_t cvxpnpl_b200_workspace_bytes(int64_t batch)
     return ws_bytes_for(device_slots(batch), batch);
 }
 
-int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
+// mode 0: the whole path; mode 1: pre-pass only, for problems [first, first + count) (the workspace
+// header is reset when first == 0); mode 2 (desc.skip_prepass): everything after the pre-pass
+static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_t first, int64_t count)
 {
     g_launches = 0;
     if (int rc = check_common(d)) return rc;
@@ -974,9 +976,12 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     const int grace = d->handoff < 0 ? -1 : (d->handoff > 0 ? d->handoff : (d->batch <= n_sm * 2 * (NT_W / 32) ? 1 : 40));
     const Opts o = make_opts(d);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e0 = cudaMemsetAsync(ctrl, 0, WS_HEADER_DOUBLES * sizeof(double), st);
-    if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
-    const bool tm = d->timing != 0;
+    if (mode == 1 && (first < 0 || count < 0 || first + count > d->batch)) return fail(-2, "pre-pass range outside the batch");
+    if (mode != 2 && (mode == 0 || first == 0)) {
+        cudaError_t e0 = cudaMemsetAsync(ctrl, 0, WS_HEADER_DOUBLES * sizeof(double), st);
+        if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
+    }
+    const bool tm = d->timing != 0 && mode != 1;
     g_ev_n = 0;
     // regions behind the hand-over slab (see ws_bytes_for)
     double* warm = (double*)((uint32_t*)(slab + slots * cvx::HAND_DOUBLES) + slots * cvx::AA_WORDS);
@@ -986,10 +991,21 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     unsigned* bucket_count = (unsigned*)(ctrl + 16);
     unsigned* bucket_offset = bucket_count + N_BUCKETS;
     mark(tm, 0, st);
-    pre_kernel<<<(unsigned)((d->batch + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(dd, o, pre, bucket_count, bucket_of);
+    if (mode != 2) {
+        const int64_t lo = mode == 1 ? first : 0, hi = mode == 1 ? first + count : d->batch;
+        if (hi > lo)
+            pre_kernel<<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(dd, o, pre, bucket_count,
+                                                                                         bucket_of, lo, hi);
+        if (mode == 1) {
+            g_launches = 1;
+            cudaError_t e1 = cudaGetLastError();
+            if (e1 != cudaSuccess) return fail((int)e1, cudaGetErrorString(e1));
+            return 0;
+        }
+    }
     bucket_scan_kernel<<<1, 32, 0, st>>>(bucket_count, bucket_offset);
     bucket_scatter_kernel<<<(unsigned)((d->batch + 255) / 256), 256, 0, st>>>(d->batch, bucket_of, bucket_offset, order);
-    g_launches = 5;
+    g_launches = (mode == 2) ? 4 : 5;   // pre-pass, two sort kernels, solver, finish
     const double* warm_in = nullptr;
     if (d->fp32_iters > 0) {
         // FP32 first phase, then its bases made orthonormal in FP64
@@ -1029,6 +1045,16 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     return 0;
+}
+
+int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* d, void* stream)
+{
+    return solve_impl(d, stream, (d && d->skip_prepass) ? 2 : 0, 0, 0);
+}
+
+int cvxpnpl_b200_prepass(const cvxpnpl_b200_desc* d, int64_t first, int64_t count, void* stream)
+{
+    return solve_impl(d, stream, 1, first, count);
 }
 
 int cvxpnpl_b200_kernel_times(float* ms, int n)

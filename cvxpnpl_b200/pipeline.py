@@ -8,10 +8,12 @@ the packed `[B, 15]` pose record of `cvxpnpl_b200.distributed` in a pinned host
 tensor.  Plumbing only (torch streams / events); the arithmetic is
 `solve_batched`.
 """
+import ctypes
 from typing import Dict, Optional
 
 import torch
 
+from . import _lib
 from .batched import BatchedPoses, Workspace, solve_batched
 from .distributed import RECORD, pack_record
 
@@ -72,3 +74,60 @@ class HostPipeline:
         self.host_out.copy_(pack_record(o.R[:, 0], o.t[:, 0], o.n_poses, o.status, o.iters), non_blocking=True)
         self.cur = 1 - slot
         return self.host_out
+
+
+class HostStager:
+    """One batch from pinned HOST memory with the copy hidden as far as a single step allows:
+    the correspondences go up in `chunks` slices on a copy stream and the pre-pass kernel
+    (assembly + start decomposition, `cvxpnpl_b200_prepass`) of each slice runs as soon as
+    that slice has landed, i.e. under the copies of the following slices.  Everything after
+    the pre-pass needs the whole batch and follows on the current stream."""
+
+    def __init__(self, K, device, chunks=4, **solve_kwargs):
+        self.device = torch.device(device)
+        self.K = torch.as_tensor(K, dtype=torch.float64).to(self.device)
+        self.chunks = int(chunks)
+        self.kw = solve_kwargs
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.buf = None
+        self.ws = None
+        self.out = None
+        self.done = None     # event: the previous solve no longer reads the input buffers
+
+    def solve(self, host: Dict[str, torch.Tensor]) -> BatchedPoses:
+        host = {k: v for k, v in host.items() if v is not None and v.shape[1] > 0}
+        B = next(iter(host.values())).shape[0]
+        if self.buf is None or next(iter(self.buf.values())).shape[0] != B:
+            self.buf = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
+            self.ws, self.out = Workspace(B, self.device), None
+        main = torch.cuda.current_stream(self.device)
+        bounds = [(c * B) // self.chunks for c in range(self.chunks + 1)]
+        events = []
+        entry = torch.cuda.Event()
+        entry.record(main)       # the copies start after everything already queued on the caller's stream
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(entry)
+            if self.done is not None:
+                self.copy_stream.wait_event(self.done)
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                for k, v in host.items():
+                    self.buf[k][lo:hi].copy_(v[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                events.append(ev)
+
+        def hook(lib, d, stream):
+            n = 0
+            for ev, lo, hi in zip(events, bounds[:-1], bounds[1:]):
+                main.wait_event(ev)
+                if hi > lo:
+                    _lib.check(lib.cvxpnpl_b200_prepass(ctypes.byref(d), lo, hi - lo, ctypes.c_void_p(stream)))
+                    n += 1
+            return n
+
+        self.out = solve_batched(self.K, pts_2d=self.buf.get("pts_2d"), pts_3d=self.buf.get("pts_3d"),
+                                 line_2d=self.buf.get("line_2d"), line_3d=self.buf.get("line_3d"), workspace=self.ws,
+                                 out=self.out, _prepass_hook=hook, **self.kw)
+        self.done = torch.cuda.Event()
+        self.done.record(main)
+        return self.out

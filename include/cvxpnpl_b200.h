@@ -86,6 +86,8 @@ typedef struct cvxpnpl_b200_desc {
                                extraction" (configs[3]): the iterations that bring a problem into the linear
                                tail run in FP32 (at most this many), the FP64 solver finishes to `eps` */
     int32_t timing;         /* != 0: record CUDA events between the kernels of `solve` (cvxpnpl_b200_kernel_times) */
+    int32_t skip_prepass;   /* != 0: the pre-pass of every problem has been run by cvxpnpl_b200_prepass already */
+    int32_t reserved3;
 } cvxpnpl_b200_desc;
 
 /* library version string, e.g. "cvxpnpl_b200 0.1.0 (sm_100a)" */
@@ -101,6 +103,12 @@ size_t cvxpnpl_b200_workspace_bytes(int64_t batch);
  * success, a negative value for bad arguments, a positive cudaError_t otherwise.
  * `stream` is a cudaStream_t.  Asynchronous. */
 int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* desc, void* stream);
+
+/* Pre-pass (assembly + start decomposition) of problems [first, first + count) only, so a caller that
+ * streams the correspondences from the host can run it chunk by chunk under the copies; call it for
+ * every problem of the batch (the chunk with first == 0 first: it resets the workspace header), then
+ * `solve` with desc.skip_prepass = 1.  Same descriptor, same workspace. */
+int cvxpnpl_b200_prepass(const cvxpnpl_b200_desc* desc, int64_t first, int64_t count, void* stream);
 
 /* Device time of each kernel of the last `solve` issued by this host thread with
  * desc.timing != 0, in ms: pre, admm32, ortho, solve_fused, straggler, resume, finish

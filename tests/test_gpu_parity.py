@@ -493,3 +493,23 @@ def test_host_pipeline_matches_direct_solve(cb):
         assert ok.float().mean() > 0.99
         assert float((R[ok] - ref.R[:, 0].cpu()[ok]).abs().max()) < 1e-7
         assert float((t[ok] - ref.t[:, 0].cpu()[ok]).abs().max()) < 1e-7
+
+
+def test_host_stager_matches_direct_solve(cb):
+    """HostStager (chunked H2D with the pre-pass of each slice under the next copies, through
+    cvxpnpl_b200_prepass + desc.skip_prepass) gives the same result as a direct solve."""
+    from cvxpnpl_b200 import synth
+    for n_pts, n_lines, B in ((8, 4, 30001), (0, 6, 5000), (8, 0, 3)):
+        d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=321)
+        host = {k: torch.from_numpy(d[k]).pin_memory() for k in ("pts_2d", "pts_3d", "line_2d", "line_3d")}
+        stager = cb.HostStager(d["K"], "cuda:0", chunks=4)
+        for _ in range(2):                       # second call reuses the buffers
+            res = stager.solve(host)
+        torch.cuda.synchronize()
+        ref = _solve(cb, d, n_pts, n_lines)
+        ok = (((ref.status & 0xFF) == 0) & ((res.status & 0xFF) == 0)).cpu().numpy()
+        assert ok.mean() > 0.9
+        assert float((res.R[:, 0] - ref.R[:, 0]).abs().cpu()[ok].max()) < 1e-7
+        assert float((res.t[:, 0] - ref.t[:, 0]).abs().cpu()[ok].max()) < 1e-7
+        n_slices = len({(c * B) // 4 for c in range(5)}) - 1     # non-empty slices
+        assert res.launches == ref.launches + n_slices - 1        # one pre-pass launch per slice instead of one
