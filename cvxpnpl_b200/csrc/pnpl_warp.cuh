@@ -78,6 +78,7 @@ CVX_HD int64_t problem_resume(const double* h, Arr<S> V, Arr<S> M, Arr<S> L, QRT
     st.finite = true;
     st.iterating = false;
     st.res_prev = 1e300;
+    st.plat = 0;
     aa_reset(st.aa);
     return (int64_t)h[HO_B];
 }
@@ -229,6 +230,7 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
     bool have_prev = false;
     int wslot = 0;
     double res_prev = 1e300;
+    int32_t plat = 0;   // plateau detector (warp-uniform; restarts at the hand-over)
     converged = false;
     for (;;) {
         // ---- 1. Z = V max(L,0) V',  W = 2 Z - M - Q/rho  (W into X) -------------------
@@ -313,7 +315,21 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
         if (it >= o.max_iters) break;
         __syncwarp();
         // ---- 4. Anderson acceleration in the tail (same rules as pass_dr / aa_step) ------
-        if (o.anderson) {
+        // plateau jump (same rule as pass_dr: plateau_update); Z holds the step g
+        const int tau = o.anderson ? plateau_update(plat, res, res_prev) : 0;
+        if (tau > 0) {
+            const double ft = (double)tau;
+            _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
+                const int r = er[q], c = ec[q];
+                const double m = fma(ft, S.Z[r * 10 + c], S.M[r * 10 + c]);
+                S.M[r * 10 + c] = m;
+                S.M[c * 10 + r] = m;
+            }
+            mask = 0u;
+            have_prev = false;
+            res_prev = res;
+            __syncwarp();
+        } else if (o.anderson) {
             const bool tail = res < o.aa_on2;
             if (!tail || res > 4.0 * res_prev) {
                 mask = 0u;

@@ -425,6 +425,30 @@ def test_straggler_warp_path_matches_thread_path(cb, n_pts, n_lines):
     assert np.median(iw) <= 1.3 * np.median(ia) + 10
 
 
+@pytest.mark.parametrize("handoff", [-1, 1])
+def test_plateau_jump_hard_problems(cb, handoff):
+    """tests/golden/hard_pnpl.npz: plateau walkers (247-799 DR iterations without the plateau jump of
+    pass_dr / the warp kernel).  Thread path (handoff=-1) and warp path (handoff=1): fewer than half the
+    iterations, poses equal to the oracle's."""
+    import os
+    import warnings
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    h = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "hard_pnpl.npz")))
+    res = _solve(cb, h, 8, 4, handoff=handoff)
+    it = res.iters.cpu().numpy()
+    assert ((res.status & 0xFF) == 0).all() and (res.n_poses == 1).all()
+    assert it.max() <= 400 and it.sum() <= 0.5 * h["iters_without_jump"].sum(), it
+    R, t = res.R[:, 0].cpu().numpy(), res.t[:, 0].cpu().numpy()
+    for i in range(len(it)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Ro, to = orc.pnpl(h["pts_2d"][i], h["line_2d"][i], h["pts_3d"][i], h["line_3d"][i], h["K"],
+                              max_iters=400000)[0]
+        assert synth.rotation_angle(Ro, R[i]) <= ROT_TOL
+        assert np.linalg.norm(to - t[i]) / np.linalg.norm(to) <= T_TOL
+
+
 @pytest.mark.parametrize("n_pts,n_lines", [(0, 6), (8, 4)])
 def test_fp32_admm_matches_oracle(cb, n_pts, n_lines):
     """BASELINE.json configs[3]: fp32 ADMM + fp64 extraction (PnL, 6 lines) -- and the

@@ -34,6 +34,25 @@ def test_host_core_vs_oracle(n_pts, n_lines):
         assert abs(r["obj"][i, 0] - r["obj"][i, 1]) < 1e-8
 
 
+def test_host_plateau_jump_hard_problems():
+    """tests/golden/hard_pnpl.npz: the slowest PnPL problems of three 1e5 batches (plateau walkers, 247-799
+    iterations without the jump, generator tests/golden/make_hard.py).  With the plateau jump of pass_dr
+    they take less than half the iterations and land on the same optimum as the oracle."""
+    import os
+    h = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "hard_pnpl.npz")))
+    r = harness.solve(h)
+    assert (r["status"] & 0xFF == 0).all() and (r["n_poses"] == 1).all()
+    assert (r["iters"] <= 0.7 * h["iters_without_jump"]).all() and r["iters"].max() <= 320, r["iters"]
+    assert r["iters"].sum() <= 0.5 * h["iters_without_jump"].sum()
+    for i in range(len(r["iters"])):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Ro, to = orc.pnpl(h["pts_2d"][i], h["line_2d"][i], h["pts_3d"][i], h["line_3d"][i], h["K"],
+                              max_iters=400000)[0]
+        assert synth.rotation_angle(Ro, r["R"][i, 0]) < 1e-6
+        assert np.linalg.norm(to - r["t"][i, 0]) / np.linalg.norm(to) < 1e-6
+
+
 def test_host_extraction_degenerate(golden):
     g = golden["degenerate"]
     for name in ("pts4", "pts3", "lines3", "lines4", "p2l1", "coplanar8"):
