@@ -231,7 +231,6 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
     st.rho = 0.0;
     st.dobj = 0.0;
     st.res_prev = 1e300;
-    st.plat = 0;
     cvx::aa_reset(st.aa);
     int wslot = 0;   // warp-uniform history column
     for (;;) {
@@ -724,8 +723,7 @@ solve_sdp_kernel(cvxpnpl_b200_desc d, Opts o, const double* Q, uint32_t* hist, i
         st.it = 0;
         st.phase = 0;
         st.dobj = 0.0;
-        st.plat = 0;
-        cvx::aa_reset(st.aa);
+            cvx::aa_reset(st.aa);
         st.res_prev = 1e300;
         const double ir = 1.0 / st.rho;
         for (int i = 0; i < 9; ++i)

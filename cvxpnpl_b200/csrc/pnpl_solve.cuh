@@ -97,26 +97,27 @@ struct Result {
 // PnPL 8+4 55.8 / 82 / 244 -> 55.5 / 76 / 119, the 69 slowest of 3e5 PnPL problems 252 / - / 799 ->
 // 121 / - / 254, PnP-8 58.4 / 118 / 1143 -> 56.8 / 89 / 311, PnL-6 95.3 / 501 / 2500 -> 78 / 237 / 708;
 // same poses (<= 3e-9 rad).
-// `plat` packs the state: bits 0-7 flat-residual streak, bits 8-23 tau, bit 30 "jumped last time".
+// `plat` packs the state: bits 0-1 zero (LaneState::phase lives there), bits 2-9 flat-residual streak,
+// bits 10-25 tau, bit 30 "jumped last time".
 // Returns the number of steps to jump now (0: none); res, res_prev are squared residuals.
 // ---------------------------------------------------------------------------------
 CVX_HD int plateau_update(int32_t& plat, double res, double res_prev)
 {
-    int tau = (plat >> 8) & 0xffff;
+    int tau = (plat >> 10) & 0xffff;
     if (plat & PLAT_JUMPED) {
         if (res > 16.0 * res_prev) tau >>= 2;
         else if (res > 2.25 * res_prev) tau >>= 1;
         if (tau == 0) tau = PLAT_OFF;
     }
     const bool flat = fabs(res - res_prev) <= CVX_PLAT_TOL * res;
-    int streak = flat ? (plat & 0xff) + 1 : 0;
+    int streak = flat ? ((plat >> 2) & 0xff) + 1 : 0;
     streak = streak > 255 ? 255 : streak;
     if (streak >= CVX_PLAT_N && tau != PLAT_OFF) {
         tau = tau == 0 ? CVX_PLAT_TAU0 : (2 * tau > CVX_PLAT_TAU_MAX ? CVX_PLAT_TAU_MAX : 2 * tau);
-        plat = (tau << 8) | PLAT_JUMPED;
+        plat = (tau << 10) | PLAT_JUMPED;
         return tau;
     }
-    plat = (tau << 8) | streak;
+    plat = (tau << 10) | (streak << 2);
     return 0;
 }
 
@@ -144,8 +145,10 @@ struct LaneState {
     // (scaled) iterate; 2: eigen-decomposition of the unscaled Z (only when sigma != 1
     // and the solution may have rank > 1)
     int32_t phase;
+    // While phase == 0 no code looks at `phase`, so its upper bits carry the plateau detector
+    // (plateau_update; a register the 255-register solver kernel does not have to spare): every
+    // `st.phase = ...` clears it.
     bool finite, iterating, converged;
-    int32_t plat;      // plateau detector: flat-residual streak (low byte) and last jump length (see pass_dr)
     AAState aa;
 };
 
@@ -295,7 +298,6 @@ CVX_HD void problem_begin(const double* pre, const Opts& o, Arr<S> V, Arr<S> M, 
     st.dobj = 0.0;
     st.phase = 0;
     st.it = 0;
-    st.plat = 0;
     aa_reset(st.aa);
     st.res_prev = 1e300;
     st.finite = finite;
@@ -437,7 +439,6 @@ CVX_HD void problem_begin_warm(const double* pre, const double* w, const Opts& o
     st.dobj = 0.0;
     st.phase = 0;
     st.it = (int32_t)w[165];
-    st.plat = 0;
     aa_reset(st.aa);
     st.res_prev = 1e300;
     st.finite = isfinite(rho);
@@ -478,7 +479,7 @@ CVX_HD bool pass_dr(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT Q
     if (!o.anderson) return false;
     // plateau jump (see plateau_update): T holds the step g
     {
-        const int tau = plateau_update(st.plat, res, st.res_prev);
+        const int tau = plateau_update(st.phase, res, st.res_prev);
         if (tau > 0) {
             const double ft = (double)tau;
 #pragma unroll 1

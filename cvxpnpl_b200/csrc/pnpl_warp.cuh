@@ -78,7 +78,6 @@ CVX_HD int64_t problem_resume(const double* h, Arr<S> V, Arr<S> M, Arr<S> L, QRT
     st.finite = true;
     st.iterating = false;
     st.res_prev = 1e300;
-    st.plat = 0;
     aa_reset(st.aa);
     return (int64_t)h[HO_B];
 }
