@@ -106,6 +106,15 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def workload_name(B, n_pts, n_lines, admm, noise):
+    """config.workload, shared by both arms (the reference arm runs a bounded sample of it)."""
+    kind = "PnPL" if (n_pts and n_lines) else ("PnP" if n_pts else "PnL")
+    cfg_name = {(8, 4): "BASELINE.json configs[2]", (8, 0): "BASELINE.json configs[1]",
+                (0, 6): "BASELINE.json configs[3]"}.get((n_pts, n_lines), "not a BASELINE.json config")
+    return (f"{B} x {kind} ({n_pts} pts + {n_lines} lines) per GPU, "
+            f"{'fp64' if admm == 'f64' else 'fp32 ADMM first phase + fp64'}, sigma={noise}px, Kinect K ({cfg_name})")
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,8 +142,9 @@ def run_reference(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"PnPL {a.n_pts} pts + {a.n_lines} lines, sigma={a.noise}px, Kinect K",
-                   "problems_per_step": sample},
+        "config": {"workload": workload_name(a.batch, a.n_pts, a.n_lines, "f64", a.noise),
+                   "problems_per_gpu_per_step": a.batch, "eps": 1e-9, "max_iters": 2500,
+                   "sample_problems_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -351,18 +361,13 @@ def run_ours(a):
         value = total / (ms_dev * 1e-3)
         e2e = total / (ms_e2e * 1e-3)
         bpp = BYTES_PER_PROBLEM.get((n_pts, n_lines), 8 * (5 * n_pts + 10 * n_lines) + 96)
-        kind = "PnPL" if (n_pts and n_lines) else ("PnP" if n_pts else "PnL")
-        cfg_name = {(8, 4): "BASELINE.json configs[2]", (8, 0): "BASELINE.json configs[1]",
-                    (0, 6): "BASELINE.json configs[3]"}.get((n_pts, n_lines), "not a BASELINE.json config")
         achieved = bpp * B / (kernel_ms[dominant] * 1e-3) / 1e9
         flops = kc.get("fp64_flops_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if a.admm == "f64" else "f32 first phase + f64 tail/extraction", "data": "synthetic",
-            "config": {"workload": f"{B} x {kind} ({n_pts} pts + {n_lines} lines) per GPU, "
-                                   f"{'fp64' if a.admm == 'f64' else 'fp32 ADMM first phase + fp64'}, sigma={a.noise}px, "
-                                   f"Kinect K ({cfg_name})",
+            "config": {"workload": workload_name(B, n_pts, n_lines, a.admm, a.noise),
                        "problems_per_gpu_per_step": B, "eps": 1e-9, "max_iters": 2500,
                        "l2": "flushed between timed iterations (256 MB write)",
                        "collective": "all_gather of [B,15] pose records (NCCL)" if world > 1 else "none"},
