@@ -313,7 +313,7 @@ admm32_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const doubl
     cvx::ArrT<NT32, float> T{smf + (size_t)155 * NT32 + tid};
     cvx::ArrT<NT32, float> L{smf + (size_t)211 * NT32 + tid};
     cvx::GArrT<float> QR{qr32 + slot, stride32};
-    const float thr2 = (float)o.aa_on2;
+    const float thr2 = (float)cvx::FP32_EXIT_RES2;
     int64_t b = -1;
     bool exhausted = false, finite = false;
     int it = 0;

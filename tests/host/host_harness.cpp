@@ -54,7 +54,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
                 for (;;) {
                     const float res = cvx::pass32(o, aV, aM, aT, aL, aq);
                     ++it;
-                    if (!(res > (float)o.aa_on2) || it >= fp32_iters || it >= cvx::RESCALE_AT - 1) break;
+                    if (!(res > (float)cvx::FP32_EXIT_RES2) || it >= fp32_iters || it >= cvx::RESCALE_AT - 1) break;
                 }
             cvx::problem_export32(aV, aM, aL, it, warm);
             cvx::warm_orthonormalise(warm);
