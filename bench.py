@@ -155,7 +155,11 @@ def run_reference(a):
 # GPU arm
 # ------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region.  The sampler is started -- and its
+    first sample awaited -- before the warm-up (nvidia-smi's start-up takes driver locks for a few hundred
+    ms and, started right at the timed region, it delayed one of ten steps by 4 ms in one run); only the
+    samples whose timestamp falls inside the timed region are kept."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -163,40 +167,55 @@ class ClockSampler:
         self.index = index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.index)], stdout=self.f,
+                                       "-lms", "25", "-i", str(self.index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+            return
+        t = time.time()
+        while time.time() - t < 5.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
         self.f.seek(0)
-        sm, smax, reasons = [], None, set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1]))
-                smax = float(c[2])
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[2]), float(c[3]),
+                             [nm for nm, v in zip(names, c[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        where = "timed region"
+        if not inside:   # clock skew between nvidia-smi's timestamps and time.time(): keep everything
+            inside, where = rows, "warm-up + timed region"
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": inside[-1][2] if inside else None,
+                "reasons": sorted({x for r in inside for x in r[3]}), "samples": len(sm), "window": where}
 
 
 def run_ours(a):
@@ -260,7 +279,7 @@ def run_ours(a):
         host_out.copy_(p, non_blocking=True)
         return o
 
-    def timed(fn, steps, warmup, kern_events=None):
+    def timed(fn, steps, warmup, marks=None):
         for _ in range(warmup):
             fn()
             flush.zero_()
@@ -268,6 +287,8 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if marks is not None:
+            marks.mark_begin()
         evs = []
         for _ in range(steps):
             flush.zero_()  # flush L2 between timed iterations (inputs 64 MB < 126 MB L2)
@@ -277,6 +298,8 @@ def run_ours(a):
             e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
+        if marks is not None:
+            marks.mark_end()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -290,7 +313,7 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, a.steps, a.warmup)
+    ms_dev = timed(step_device, a.steps, a.warmup, marks=sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
 
     # kernel-only times for the roofline: CUDA events recorded by the library between its
