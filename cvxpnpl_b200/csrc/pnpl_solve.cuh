@@ -22,17 +22,19 @@ struct Opts {
 };
 
 // Default DR parameters (used where the descriptor leaves them 0), measured on seeded
-// batches with the Anderson accelerator and the dual-guess start in place (mean / p99
-// iterations):  rho = 0.01 ||Q||_F, sigma = 1.5 is best from 8 points up (PnPL 8+4 56 / 77,
-// PnP-8 58 / 108); with fewer points -- lines only, minimal and near-minimal sets -- the
-// iteration is more robust with rho = 0.007 ||Q||_F, sigma = 1.25 (PnL-6 111 / 587 -> 89 / 237,
-// 4 points 474 -> 360 and 37 -> 24 of 400 at the cap, 6 points 82 / 598 -> 74 / 293).
-// Over-relaxation 1.5 is as good or better than 1.3 everywhere.
+// batches with the Anderson accelerator, the dual-guess start and the plateau jump in place
+// (host build, 3000 problems, mean / p99 iterations).  From 8 points up rho = 0.017 ||Q||_F,
+// sigma = 1.25: PnPL 8+4 52.4 / 74, PnP-8 53.8 / 86 (the landscape is flat: 0.014 ... 0.02 x
+// 1.15 ... 1.4 are all within 1 %; the earlier default 0.01 / 1.5 gives 54.5 / 75 and 55.6 / 84).
+// With fewer points -- lines only, minimal and near-minimal sets -- the iteration is more robust
+// with rho = 0.007 ||Q||_F, sigma = 1.25 (PnL-6 111 / 587 -> 89 / 237, 4 points 474 -> 360 and
+// 37 -> 24 of 400 at the cap, 6 points 82 / 598 -> 74 / 293; measured before the plateau jump).
+// Over-relaxation 1.5 is as good or better than 1.3, 1.65 and 1.8 everywhere.
 CVX_HD void default_params(int n_pts, double& rho_rel, double& alpha, double& sigma)
 {
     const bool many = n_pts >= 8;
-    if (!(rho_rel > 0)) rho_rel = many ? 0.01 : 0.007;
-    if (!(sigma > 0)) sigma = many ? 1.5 : 1.25;
+    if (!(rho_rel > 0)) rho_rel = many ? 0.017 : 0.007;
+    if (!(sigma > 0)) sigma = 1.25;
     if (!(alpha > 0)) alpha = 1.5;
 }
 
