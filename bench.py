@@ -386,6 +386,10 @@ def run_ours(a):
         bpp = BYTES_PER_PROBLEM.get((n_pts, n_lines), 8 * (5 * n_pts + 10 * n_lines) + 96)
         achieved = bpp * B / (kernel_ms[dominant] * 1e-3) / 1e9
         flops = kc.get("fp64_flops_per_launch")
+        if flops and kc.get("iters_mean_at_capture"):
+            # the count is per launch of the captured build; FP64 work is proportional to the DR
+            # iterations, so a batch that needs fewer / more of them is scaled accordingly
+            flops = flops * float(iters.mean()) / kc["iters_mean_at_capture"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

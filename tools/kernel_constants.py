@@ -1,7 +1,7 @@
 """Dev tool: profiles/r1_kernel_constants.json from an ncu report of tools/prof_run.py.
     ncu -i rep.ncu-rep --page raw --csv > raw.csv
     ncu -i rep.ncu-rep --page source --csv --print-source sass --kernel-name regex:solve_fused > src.csv
-    python tools/kernel_constants.py raw.csv src.csv "<source note>" > profiles/r1_kernel_constants.json
+    python tools/kernel_constants.py raw.csv src.csv "<source note>" <mean iterations> > profiles/r1_kernel_constants.json
 Thread-level FP64 flops of solve_fused_kernel<false> = 2 DFMA + DMUL + DADD, counted per SASS line
 ("Predicated-On Thread Instructions Executed")."""
 import csv
@@ -9,6 +9,7 @@ import json
 import sys
 
 raw, src, note = sys.argv[1], sys.argv[2], sys.argv[3]
+iters_mean = float(sys.argv[4]) if len(sys.argv) > 4 else None   # mean DR iterations of the captured batch
 rows = list(csv.reader(open(raw)))
 hdr = rows[0]
 r = next(x for x in rows[2:] if "solve_fused_kernel<0>" in x[hdr.index("Kernel Name")] or "solve_fused_kernel<(bool)0>" in x[hdr.index("Kernel Name")])
@@ -41,6 +42,7 @@ print(json.dumps({
     "thread_inst_dfma": cnt["DFMA"], "thread_inst_dmul": cnt["DMUL"], "thread_inst_dadd": cnt["DADD"],
     "fp64_flops_per_launch": flops,
     "kernel_ms_under_ncu": round(g("gpu__time_duration.sum"), 3),
+    "iters_mean_at_capture": iters_mean,
     "note": "FP64 flops (2 DFMA + DMUL + DADD, thread level) of the persistent FP64 solver kernel only; the straggler "
             "kernel is not counted.  DRAM traffic of this kernel: the 156-double pre-pass record per problem is read, "
             "the parked state and the hand-over slab written.",
