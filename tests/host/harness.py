@@ -58,3 +58,11 @@ def quartic(c):
     x = np.empty(4)
     n = lib.host_quartic(_p(c), _p(x))
     return x[:n]
+
+
+def plateau_update(plat, res2, res2_prev):
+    """plateau_update of pnpl_solve.cuh on one (state, residual) step: returns (new state, jump length)."""
+    lib = load()
+    st = ctypes.c_int32(plat)
+    tau = lib.host_plateau_update(ctypes.byref(st), ctypes.c_double(res2), ctypes.c_double(res2_prev))
+    return st.value, tau

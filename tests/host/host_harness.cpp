@@ -111,3 +111,6 @@ extern "C" int host_extract(const double* Zin, const double* Q9, const double* B
 }
 
 extern "C" int host_quartic(const double* c, double* x) { return cvx::quartic_real_parts(c, x); }
+
+// plateau detector of pass_dr / the warp kernel (pnpl_solve.cuh): returns the jump length (0: none)
+extern "C" int host_plateau_update(int32_t* plat, double res2, double res2_prev) { return cvx::plateau_update(*plat, res2, res2_prev); }

@@ -53,6 +53,43 @@ def test_host_plateau_jump_hard_problems():
         assert np.linalg.norm(to - r["t"][i, 0]) / np.linalg.norm(to) < 1e-6
 
 
+def test_plateau_detector_trust_region():
+    """plateau_update (pnpl_solve.cuh): a jump after 5 flat residuals; tau doubles while the jump kicks the
+    residual by less than 1.5x, stays above that, halves above 4x, and switches off when it shrinks to nothing."""
+    def run_flat(st, n, r=1e-6):
+        taus = []
+        for _ in range(n):
+            st, tau = harness.plateau_update(st, r, r)
+            taus.append(tau)
+        return st, taus
+    st, taus = run_flat(0, 5)
+    assert taus == [0, 0, 0, 0, 8]                      # first jump: 8 steps, after 5 flat iterations
+    st, tau = harness.plateau_update(st, 1.2e-6, 1e-6)  # kick 1.1x (squared 1.2x): tau may double
+    assert tau == 0
+    st, taus = run_flat(st, 5, 1.2e-6)
+    assert taus[-1] == 16 and sum(taus) == 16
+    st, tau = harness.plateau_update(st, 4e-6, 1.2e-6)  # kick ~1.8x: tau stays
+    st, taus = run_flat(st, 5, 4e-6)
+    assert taus[-1] == 16
+    st, tau = harness.plateau_update(st, 4e-4, 4e-6)    # kick 10x: tau halved
+    st, taus = run_flat(st, 5, 4e-4)
+    assert taus[-1] == 8
+    for _ in range(4):                                  # every jump kicks hard: 8 -> 4 -> 2 -> 1 -> off
+        st, _ = harness.plateau_update(st, 1.0, 1e-6)
+        st, taus = run_flat(st, 5, 1.0)
+    st, _ = harness.plateau_update(st, 1.0, 1e-6)
+    st, taus = run_flat(st, 20, 1.0)
+    assert sum(taus) == 0
+    # a residual that keeps falling never jumps
+    st, r = 0, 1.0
+    for _ in range(50):
+        st, tau = harness.plateau_update(st, r * 0.8, r)
+        r *= 0.8
+        assert tau == 0
+    # the state never touches the two phase bits of LaneState::phase
+    assert st & 3 == 0
+
+
 def test_host_extraction_degenerate(golden):
     g = golden["degenerate"]
     for name in ("pts4", "pts3", "lines3", "lines4", "p2l1", "coplanar8"):
