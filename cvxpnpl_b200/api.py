@@ -104,11 +104,44 @@ class CvxPnPL:
         return pnpl(pts_2d, line_2d, pts_3d, line_3d, K)
 
 
+def _rc_unpack(res, verbose):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # _solve_relaxation_rc (rc.py:68-122) has no optimality warning
+        return _unpack(res, verbose)
+
+
 def rc(pts_2d, pts_3d, K, eps: float = 1e-9, max_iters: int = 2500, verbose: bool = False) -> List[Pose]:
-    """The "rc" ablation of benchmarks/toolkit/methods/pnp.py:58-82 / rc.py: pnp with the
-    redundant row-orthonormality equalities removed from the SDP."""
+    """The "rc" ablation for points (benchmarks/toolkit/methods/pnp.py:58-82 -> rc.py:68-122): pnp with
+    the redundant row-orthonormality equalities removed from the SDP (16 instead of 22 equalities)."""
     res = _b.solve_batched(np.asarray(K, dtype=np.float64), pts_2d=_one(pts_2d, (2,)), pts_3d=_one(pts_3d, (3,)),
                            eps=eps, max_iters=max_iters, variant="rc")
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")      # rc.py has no optimality warning
-        return _unpack(res, verbose)
+    return _rc_unpack(res, verbose)
+
+
+rc_pnp = rc
+
+
+def rc_pnl(line_2d, line_3d, K, eps: float = 1e-9, max_iters: int = 2500, verbose: bool = False) -> List[Pose]:
+    """The "rc" ablation for lines (benchmarks/toolkit/methods/pnl.py:11-34 -> rc.py:68-122)."""
+    res = _b.solve_batched(np.asarray(K, dtype=np.float64), line_2d=_one(line_2d, (2, 2)),
+                           line_3d=_one(line_3d, (2, 3)), eps=eps, max_iters=max_iters, variant="rc")
+    return _rc_unpack(res, verbose)
+
+
+def rc_pnpl(pts_2d, line_2d, pts_3d, line_3d, K, eps: float = 1e-9, max_iters: int = 2500,
+            verbose: bool = False) -> List[Pose]:
+    """The "rc" ablation for points and lines (benchmarks/toolkit/methods/pnpl.py:12-46 -> rc.py:68-122)."""
+    kw = {}
+    if np.size(pts_2d):
+        kw.update(pts_2d=_one(pts_2d, (2,)), pts_3d=_one(pts_3d, (3,)))
+    if np.size(line_2d):
+        kw.update(line_2d=_one(line_2d, (2, 2)), line_3d=_one(line_3d, (2, 3)))
+    res = _b.solve_batched(np.asarray(K, dtype=np.float64), eps=eps, max_iters=max_iters, variant="rc", **kw)
+    return _rc_unpack(res, verbose)
+
+
+def null(pts_2d, pts_3d, K) -> List[Pose]:
+    """The "null" ablation (benchmarks/toolkit/methods/pnp.py:24-55): no SDP, the smallest right singular
+    vector of A projected onto SO(3)."""
+    res = _b.null_batched(_one(pts_2d, (2,)), _one(pts_3d, (3,)), np.asarray(K, dtype=np.float64))
+    return [(res.R[0, 0].cpu().numpy().copy(), res.t[0, 0].cpu().numpy().copy())]

@@ -57,7 +57,9 @@ class Workspace:
 
     def __init__(self, batch, device):
         lib = _lib.load()
-        self.nbytes = int(lib.cvxpnpl_b200_workspace_bytes(batch))
+        device = torch.device(device)
+        with torch.cuda.device(device):   # the size depends on the SM count of the device it is for
+            self.nbytes = int(lib.cvxpnpl_b200_workspace_bytes(batch))
         self.buf = torch.empty(max(self.nbytes // 8, 1), dtype=torch.float64, device=device)
 
 
@@ -113,23 +115,39 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
     if k_batched and K.shape[0] != B:
         raise ValueError("batched K must be [B,3,3]")
 
+    if variant not in ("full", "rc"):
+        raise ValueError("variant must be 'full' or 'rc'")
+    if admm_dtype not in ("f64", "f32"):
+        raise ValueError("admm_dtype must be 'f64' or 'f32'")
     n_corr = (pts_2d.shape[1] if have_p else 0) + (line_2d.shape[1] if have_l else 0)
     if n_corr >= LARGE_N and B > 0:
         # many correspondences per problem (benchmarks/scalability/pnp.py:37-40): the
         # assembly is a bandwidth-bound streaming reduction with its own kernels; the
-        # SDP and the extraction then run as stages on the [B,9,9] / [B,10,10] matrices
+        # SDP and the extraction then run as stages on the [B,9,9] / [B,10,10] matrices.
+        # Options that only exist on the fused path are refused, never silently dropped.
+        unsupported = [name for name, given in (("admm_dtype='f32'", admm_dtype != "f64"), ("out", out is not None),
+                                                ("handoff", handoff != 0), ("timing", bool(timing)),
+                                                ("_prepass_hook", _prepass_hook is not None)) if given]
+        if unsupported:
+            raise NotImplementedError(f"{', '.join(unsupported)}: not available with >= {LARGE_N} correspondences per "
+                                      "problem (streaming assembly + stage kernels)")
         with torch.cuda.device(device):
             Q, Bm = assemble_batched(K, pts_2d if have_p else None, pts_3d if have_p else None,
                                      line_2d if have_l else None, line_3d if have_l else None)
+            launches = int(lib.cvxpnpl_b200_last_launch_count())
             Z, dobj, iters, status = solve_sdp_batched(Q, eps=eps, max_iters=max_iters, sweeps=sweeps, rho_rel=rho_rel,
-                                                       alpha=alpha, sigma=sigma, anderson=anderson,
+                                                       alpha=alpha, sigma=sigma, anderson=anderson, variant=variant,
                                                        n_pts=pts_2d.shape[1] if have_p else 0)
+            launches += int(lib.cvxpnpl_b200_last_launch_count())
             res = extract_batched(Z, Q, Bm, dobj, eps=eps)
+            launches += int(lib.cvxpnpl_b200_last_launch_count())
             res.iters = iters
             # keep the solver's status (MAX_ITERS / NaN) where extraction itself succeeded
             res.status = torch.where((res.status & ST_CODE_MASK) == ST_OK, res.status | status, res.status)
             res.Z = Z if return_Z else None
-            res.launches = 4
+            if not return_obj:
+                res.obj = None
+            res.launches = launches
         return res
     with torch.cuda.device(device):
         if out is None:
@@ -219,10 +237,10 @@ def assemble_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None):
 
 
 def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True,
-                      n_pts=8):
+                      n_pts=8, variant="full"):
     """Q [B,9,9] -> (Z [B,10,10], dobj [B], iters [B], status [B]); the scs.solve
-    call of cvxpnpl.py:478-492.  n_pts (points behind each Q) only selects the default
-    rho / sigma where they are left 0."""
+    call of cvxpnpl.py:478-492 (variant="rc": of benchmarks/toolkit/methods/rc.py:90-96).
+    n_pts (points behind each Q) only selects the default rho / sigma where they are left 0."""
     _require_cuda()
     lib = _lib.load()
     device = torch.device("cuda", torch.cuda.current_device())
@@ -239,6 +257,7 @@ def solve_sdp_batched(Q, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=
     d.eps, d.max_iters, d.sweeps, d.rho_rel, d.alpha = float(eps), int(max_iters), int(sweeps), float(rho_rel), float(alpha)
     d.sigma = float(sigma)
     d.anderson = 0 if anderson else -1
+    d.variant = {"full": 0, "rc": 1}[variant]
     d.Z, d.obj, d.iters, d.status = _ptr(Z), _ptr(obj), _ptr(iters), _ptr(status)
     d.workspace, d.workspace_bytes = _ptr(ws.buf), ws.nbytes
     stream = torch.cuda.current_stream(device).cuda_stream

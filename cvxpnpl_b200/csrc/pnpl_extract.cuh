@@ -13,131 +13,165 @@ namespace cvx {
 
 // ---- real parts of the four roots of  c4 x^4 + c3 x^3 + c2 x^2 + c1 x + c0 ------
 // (cvxpnpl.py:185-186: np.roots, then np.real of ALL roots, complex ones included)
-// Ferrari factorisation into two real quadratics + Newton polish of real roots.
-// Returns the number of roots (4, or fewer when leading coefficients vanish).
+// np.roots is backward stable (companion-matrix eigenvalues), also for the badly scaled
+// quartics this branch produces (leading coefficient 1e-5 of the others: one root at 1e5,
+// three near 1e-2).  Here: Ferrari's factorisation into two quadratics gives four complex
+// starting points, the Aberth-Ehrlich simultaneous iteration on the ORIGINAL polynomial
+// then converges to all four roots to working precision (Ferrari alone loses the small
+// roots of such a quartic to cancellation in the depressing shift).
+struct Cplx {
+    double re, im;
+};
+CVX_HD Cplx c_add(Cplx a, Cplx b) { return Cplx{a.re + b.re, a.im + b.im}; }
+CVX_HD Cplx c_sub(Cplx a, Cplx b) { return Cplx{a.re - b.re, a.im - b.im}; }
+CVX_HD Cplx c_mul(Cplx a, Cplx b) { return Cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+CVX_HD Cplx c_div(Cplx a, Cplx b)
+{
+    // Smith's algorithm (no overflow of |b|^2)
+    if (fabs(b.re) >= fabs(b.im)) {
+        const double r = b.im / b.re, den = b.re + b.im * r;
+        return Cplx{(a.re + a.im * r) / den, (a.im - a.re * r) / den};
+    }
+    const double r = b.re / b.im, den = b.re * r + b.im;
+    return Cplx{(a.re * r + a.im) / den, (a.im * r - a.re) / den};
+}
+CVX_HD double c_abs1(Cplx a) { return fabs(a.re) + fabs(a.im); }
+
+// Aberth-Ehrlich on a degree-n polynomial (ascending coefficients c[0..n], c[n] != 0), n <= 4
+CVX_HD void aberth_polish(const double* c, int n, Cplx* z)
+{
+    for (int it = 0; it < 80; ++it) {
+        Cplx w[4];
+        double worst = 0.0;
+        for (int k = 0; k < n; ++k) {
+            // p(z_k), p'(z_k) by Horner; for |z| > 1 on the reversed polynomial (no overflow, and the
+            // Newton ratio of a huge root keeps its accuracy): p(z) = z^n q(1/z)
+            Cplx nr;   // Newton ratio p / p'
+            if (c_abs1(z[k]) <= 1.0) {
+                Cplx pv{c[n], 0.0}, dv{0.0, 0.0};
+                for (int e = n - 1; e >= 0; --e) {
+                    dv = c_add(c_mul(dv, z[k]), pv);
+                    pv = c_add(c_mul(pv, z[k]), Cplx{c[e], 0.0});
+                }
+                if (pv.re == 0.0 && pv.im == 0.0) { w[k] = Cplx{0.0, 0.0}; continue; }
+                nr = c_div(pv, dv);
+            } else {
+                const Cplx u = c_div(Cplx{1.0, 0.0}, z[k]);
+                Cplx qv{c[0], 0.0}, dq{0.0, 0.0};
+                for (int e = 1; e <= n; ++e) {
+                    dq = c_add(c_mul(dq, u), qv);
+                    qv = c_add(c_mul(qv, u), Cplx{c[e], 0.0});
+                }
+                if (qv.re == 0.0 && qv.im == 0.0) { w[k] = Cplx{0.0, 0.0}; continue; }
+                // p'/p = n/z - u^2 q'(u)/q(u)  =>  p/p' = 1 / (n u - u^2 q'/q)
+                const Cplx t = c_sub(Cplx{(double)n * u.re, (double)n * u.im}, c_mul(c_mul(u, u), c_div(dq, qv)));
+                nr = c_div(Cplx{1.0, 0.0}, t);
+            }
+            Cplx sum{0.0, 0.0};
+            for (int j = 0; j < n; ++j) {
+                if (j == k) continue;
+                Cplx df = c_sub(z[k], z[j]);
+                if (df.re == 0.0 && df.im == 0.0) df = Cplx{1e-18 * (1.0 + c_abs1(z[k])), 1e-18 * (1.0 + c_abs1(z[k]))};
+                sum = c_add(sum, c_div(Cplx{1.0, 0.0}, df));
+            }
+            const Cplx den = c_sub(Cplx{1.0, 0.0}, c_mul(nr, sum));
+            w[k] = (den.re == 0.0 && den.im == 0.0) ? nr : c_div(nr, den);
+            if (!isfinite(w[k].re) || !isfinite(w[k].im)) w[k] = Cplx{0.0, 0.0};
+            worst = fmax(worst, c_abs1(w[k]) / fmax(c_abs1(z[k]), 1e-300));
+        }
+        for (int k = 0; k < n; ++k) z[k] = c_sub(z[k], w[k]);
+        if (worst <= 4e-16) break;
+    }
+}
+
+// the two roots of x^2 + b x + c as complex numbers
+CVX_HD void quadratic_roots(double b, double c, Cplx& r0, Cplx& r1)
+{
+    const double disc = b * b - 4 * c;
+    if (disc >= 0) {
+        const double t = -0.5 * (b + copysign(sqrt(disc), b));
+        r0 = Cplx{t, 0.0};
+        r1 = Cplx{(t != 0.0) ? c / t : 0.0, 0.0};
+    } else {
+        r0 = Cplx{-0.5 * b, 0.5 * sqrt(-disc)};
+        r1 = Cplx{-0.5 * b, -0.5 * sqrt(-disc)};
+    }
+}
+
+// Returns the number of roots (4, or fewer when leading coefficients vanish exactly, like np.roots).
 CVX_HD int quartic_real_parts(const double c[5], double x[4])
 {
-    // strip vanishing leading coefficients like np.roots does for exact zeros
-    if (c[4] == 0.0) {
-        if (c[3] == 0.0) {
-            if (c[2] == 0.0) {
-                if (c[1] == 0.0) return 0;
-                x[0] = -c[0] / c[1];
-                return 1;
-            }
-            const double disc = c[1] * c[1] - 4 * c[2] * c[0];
-            if (disc >= 0) {
-                const double s = sqrt(disc);
-                x[0] = (-c[1] + s) / (2 * c[2]);
-                x[1] = (-c[1] - s) / (2 * c[2]);
-            } else {
-                x[0] = x[1] = -c[1] / (2 * c[2]);
-            }
-            return 2;
-        }
-        // cubic: deflate one real root found by Newton from outside the root bound
+    int n = 4;
+    while (n > 0 && c[n] == 0.0) --n;
+    if (n == 0) return 0;
+    Cplx z[4];
+    if (n == 1) {
+        x[0] = -c[0] / c[1];
+        return 1;
+    }
+    if (n == 2) {
+        quadratic_roots(c[1] / c[2], c[0] / c[2], z[0], z[1]);
+    } else if (n == 3) {
+        // cubic: one real root by Newton from outside the root bound, then the quadratic factor
         const double a = c[2] / c[3], b = c[1] / c[3], d = c[0] / c[3];
         double r = 1.0 + fmax(fabs(a), fmax(fabs(b), fabs(d)));
         for (int it = 0; it < 200; ++it) {
             const double f = ((r + a) * r + b) * r + d, fp = (3 * r + 2 * a) * r + b;
             const double dr = f / fp;
             r -= dr;
-            if (fabs(dr) <= 1e-16 * fabs(r)) break;
+            if (!(fabs(dr) > 1e-16 * fabs(r))) break;
         }
-        x[0] = r;
-        const double qb = a + r, qc = b + r * qb;  // x^2 + qb x + qc
-        const double disc = qb * qb - 4 * qc;
-        if (disc >= 0) {
-            const double s = sqrt(disc);
-            x[1] = 0.5 * (-qb + s);
-            x[2] = 0.5 * (-qb - s);
-        } else {
-            x[1] = x[2] = -0.5 * qb;
-        }
-        return 3;
-    }
-    const double a = c[3] / c[4], b = c[2] / c[4], cc = c[1] / c[4], d = c[0] / c[4];
-    const double sh = 0.25 * a;
-    // depressed quartic y^4 + p y^2 + q y + r, x = y - a/4
-    const double p = b - 6 * sh * sh;
-    const double q = cc - 2 * b * sh + 8 * sh * sh * sh;
-    const double r = d - cc * sh + b * sh * sh - 3 * sh * sh * sh * sh;
-    double y[4];
-    bool is_real[4];
-    const double scale = fmax(fmax(fabs(p), sqrt(fabs(r))), 1e-300);
-    if (fabs(q) <= 1e-14 * scale * sqrt(scale)) {
-        // biquadratic: y^2 = (-p +- sqrt(p^2 - 4r)) / 2
-        const double disc = p * p - 4 * r;
-        if (disc >= 0) {
-            const double s = sqrt(disc);
-            const double u[2] = {0.5 * (-p + s), 0.5 * (-p - s)};
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (u[k] >= 0) {
-                    y[2 * k] = sqrt(u[k]); y[2 * k + 1] = -sqrt(u[k]);
-                    is_real[2 * k] = is_real[2 * k + 1] = true;
-                } else {
-                    y[2 * k] = y[2 * k + 1] = 0.0;  // purely imaginary pair
-                    is_real[2 * k] = is_real[2 * k + 1] = false;
-                }
-            }
-        } else {
-            // y^2 complex: y = +-sqrt(u), u = (-p +- i sqrt(-disc))/2 ; Re sqrt(u) = sqrt((|u| + Re u)/2)
-            const double re = -0.5 * p, im = 0.5 * sqrt(-disc);
-            const double mod = sqrt(re * re + im * im);
-            const double sr = sqrt(fmax(0.5 * (mod + re), 0.0));
-            y[0] = sr; y[1] = sr; y[2] = -sr; y[3] = -sr;
-            is_real[0] = is_real[1] = is_real[2] = is_real[3] = false;
-        }
+        z[0] = Cplx{r, 0.0};
+        const double qb = a + r;
+        quadratic_roots(qb, b + r * qb, z[1], z[2]);
     } else {
-        // resolvent cubic 8 m^3 + 8 p m^2 + (2 p^2 - 8 r) m - q^2 = 0, largest (positive) root
-        const double A = p, Bc = 0.25 * p * p - r, Cc = -0.125 * q * q;  // m^3 + A m^2 + Bc m + Cc
+        const double a = c[3] / c[4], b = c[2] / c[4], cc = c[1] / c[4], d = c[0] / c[4];
+        const double sh = 0.25 * a;
+        // depressed quartic y^4 + p y^2 + q y + r, x = y - a/4
+        const double p = b - 6 * sh * sh;
+        const double q = cc - 2 * b * sh + 8 * sh * sh * sh;
+        const double r = d - cc * sh + b * sh * sh - 3 * sh * sh * sh * sh;
+        // resolvent cubic m^3 + p m^2 + (p^2/4 - r) m - q^2/8 = 0, largest real root (>= 0)
+        const double A = p, Bc = 0.25 * p * p - r, Cc = -0.125 * q * q;
         double m = 1.0 + fmax(fabs(A), fmax(fabs(Bc), fabs(Cc)));
         for (int it = 0; it < 300; ++it) {
             const double f = ((m + A) * m + Bc) * m + Cc, fp = (3 * m + 2 * A) * m + Bc;
             const double dm = f / fp;
             m -= dm;
-            if (fabs(dm) <= 1e-16 * fabs(m)) break;
+            if (!(fabs(dm) > 1e-16 * fabs(m))) break;
         }
-        m = fmax(m, 1e-300);
-        const double s2m = sqrt(2 * m);
-        const double h = q / (2 * s2m);
-        // y^2 - s2m y + (p/2 + m + h) = 0   and   y^2 + s2m y + (p/2 + m - h) = 0
-        const double lin[2] = {-s2m, s2m};
-        const double con[2] = {0.5 * p + m + h, 0.5 * p + m - h};
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const double disc = lin[k] * lin[k] - 4 * con[k];
-            if (disc >= 0) {
-                const double s = sqrt(disc);
-                // stable quadratic roots
-                const double t = -0.5 * (lin[k] + copysign(s, lin[k]));
-                y[2 * k] = t;
-                y[2 * k + 1] = (t != 0.0) ? con[k] / t : 0.0;
-                is_real[2 * k] = is_real[2 * k + 1] = true;
-            } else {
-                y[2 * k] = y[2 * k + 1] = -0.5 * lin[k];
-                is_real[2 * k] = is_real[2 * k + 1] = false;
+        if (!(m > 0.0) || !isfinite(m)) m = 0.0;
+        if (m > 0.0) {
+            const double s2m = sqrt(2 * m), h = q / (2 * s2m);
+            // y^2 - s2m y + (p/2 + m + h) = 0   and   y^2 + s2m y + (p/2 + m - h) = 0
+            quadratic_roots(-s2m, 0.5 * p + m + h, z[0], z[1]);
+            quadratic_roots(s2m, 0.5 * p + m - h, z[2], z[3]);
+        } else {
+            // biquadratic: y^2 = u with u^2 + p u + r = 0
+            Cplx u0, u1;
+            quadratic_roots(p, r, u0, u1);
+            const Cplx us[2] = {u0, u1};
+            for (int k = 0; k < 2; ++k) {
+                // principal complex square root
+                const double mod = sqrt(us[k].re * us[k].re + us[k].im * us[k].im);
+                const double sr = sqrt(fmax(0.5 * (mod + us[k].re), 0.0));
+                const double si = copysign(sqrt(fmax(0.5 * (mod - us[k].re), 0.0)), us[k].im);
+                z[2 * k] = Cplx{sr, si};
+                z[2 * k + 1] = Cplx{-sr, -si};
             }
         }
+        for (int k = 0; k < 4; ++k) z[k].re -= sh;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        double xv = y[k] - sh;
-        if (is_real[k]) {
-            // Newton polish on the original polynomial (guarded)
-            for (int it = 0; it < 3; ++it) {
-                const double f = (((c[4] * xv + c[3]) * xv + c[2]) * xv + c[1]) * xv + c[0];
-                const double fp = ((4 * c[4] * xv + 3 * c[3]) * xv + 2 * c[2]) * xv + c[1];
-                if (fp == 0.0) break;
-                const double dx = f / fp;
-                if (!(fabs(dx) < 1e-3 * (fabs(xv) + 1e-3))) break;  // near-multiple root: keep Ferrari value
-                xv -= dx;
-            }
-        }
-        x[k] = xv;
+    // separate coincident starting points (a double root would make the Aberth weights singular)
+    for (int k = 0; k < n; ++k) {
+        if (!isfinite(z[k].re) || !isfinite(z[k].im)) z[k] = Cplx{0.3 * (k + 1), 0.2 * (k + 1)};
+        const double pert = 1e-9 * (k + 1) * (1.0 + c_abs1(z[k]));
+        z[k].re += (k & 1) ? pert : -pert;
+        z[k].im += (k & 2) ? pert : -pert;
     }
-    return 4;
+    aberth_polish(c, n, z);
+    for (int k = 0; k < n; ++k) x[k] = z[k].re;
+    return n;
 }
 
 // solve the n x n system (row-major, in place) with m right-hand sides by Gaussian
@@ -393,8 +427,16 @@ CVX_HD int extract_poses(Arr<S> V, const double lam[10], QIn Q, BIn Bm, int32_t&
     if (rank == 1) {
         double rc[9];
         const double inv = 1.0 / V[90 + jmax];
+        bool fin = true;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) rc[i] = V[i * 10 + jmax] * inv;
+        for (int i = 0; i < 9; ++i) {
+            rc[i] = V[i * 10 + jmax] * inv;
+            fin = fin && isfinite(rc[i]);
+        }
+        if (!fin) {   // np.linalg.svd raises LinAlgError on a non-finite matrix (cvxpnpl.py:510)
+            status = ST_SINGULAR;
+            return 0;
+        }
         pobj = finish_pose(rc, Q, Bm, R_out, t_out);
         if (eps >= 0) certified = !(fabs(pobj - dobj) > eps);
         n = 1;
@@ -420,6 +462,14 @@ CVX_HD int extract_poses(Arr<S> V, const double lam[10], QIn Q, BIn Bm, int32_t&
             status = ST_SINGULAR;
             return 0;
         }
+        // a candidate that is not finite (e.g. the averaged quadratic of the rank-2 branch with a
+        // vanishing leading coefficient, cvxpnpl.py:307-314) makes the reference's batched
+        // np.linalg.svd raise LinAlgError for the whole call (cvxpnpl.py:510)
+        for (int c = 0; c < 9 * n; ++c)
+            if (!isfinite(rcs[c])) {
+                status = ST_SINGULAR;
+                return 0;
+            }
         for (int c = 0; c < n; ++c) {
             const double o = finish_pose(rcs + 9 * c, Q, Bm, R_out + 9 * c, t_out + 3 * c);
             if (c == 0) pobj = o;

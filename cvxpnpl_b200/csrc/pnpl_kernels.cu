@@ -17,6 +17,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/cvxpnpl_b200.h"
 #include "pnpl_core.cuh"
 #include "pnpl_extract.cuh"
@@ -58,6 +60,26 @@ int fail(int code, const char* msg)
 {
     snprintf(g_err, sizeof(g_err), "%s", msg);
     return code;
+}
+
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute belongs to the (device) context, not
+// to the process, and host threads may call into the library concurrently on different devices:
+// remember per device (bit d of a mask per kernel group) under a mutex.
+constexpr int MAX_DEVICES = 64;
+std::mutex g_attr_mutex;
+bool g_attr_done[4][MAX_DEVICES];   // groups: 0 solve path, 1 null, 2 solve_sdp stage, 3 extract stage
+
+template <class F>
+cudaError_t opt_in_once(int group, F set_all)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    if (dev >= 0 && dev < MAX_DEVICES && g_attr_done[group][dev]) return cudaSuccess;
+    e = set_all();
+    if (e == cudaSuccess && dev >= 0 && dev < MAX_DEVICES) g_attr_done[group][dev] = true;
+    return e;
 }
 
 using cvx::Opts;
@@ -576,9 +598,9 @@ constexpr int CHUNK_ELEMS = 4096;     // correspondences per CTA
 __global__ void __launch_bounds__(NT_L) accumulate_kernel(cvxpnpl_b200_desc d, double* acc_out)
 {
     __shared__ double red[NT_L / 32][60];
-    const int64_t b = blockIdx.y;
+    const int64_t b = blockIdx.x;   // problems on grid.x (up to 2^31 - 1), chunks of one problem on grid.y
     const int n_total = d.n_pts + d.n_lines;
-    const int lo = blockIdx.x * CHUNK_ELEMS;
+    const int lo = blockIdx.y * CHUNK_ELEMS;
     const int hi = min(lo + CHUNK_ELEMS, n_total);
     const double* K = problem_K(d, b);
     double Kl[9], Ki[9];
@@ -939,23 +961,24 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     if (d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch) ||
         (cvxpnpl_b200_workspace_bytes(d->batch) && !d->workspace))
         return fail(-7, "workspace too small");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(solve_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(solve_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(straggler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_P_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(admm32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM32_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_F_BYTES);
+    {
+        const cudaError_t e = opt_in_once(0, [] {
+            cudaError_t e = cudaFuncSetAttribute(solve_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)SMEM_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(solve_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(straggler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_P_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(admm32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM32_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_F_BYTES);
+            return e;
+        });
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-        attr_set = true;
     }
     const int64_t slots = device_slots(d->batch);
     // persistent grid: one CTA per SM (shared memory allows exactly one), never more
@@ -1083,11 +1106,11 @@ int cvxpnpl_b200_null(const cvxpnpl_b200_desc* d, void* stream)
         return fail(-5, "null input pointer");
     if (!d->R || !d->t || !d->n_poses || !d->status) return fail(-6, "null output pointer");
     const size_t smem = (size_t)NT_F * 227 * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(null_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        const cudaError_t e = opt_in_once(1, [smem] {
+            return cudaFuncSetAttribute(null_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-        attr_set = true;
     }
     null_kernel<<<(unsigned)((d->batch + NT_F - 1) / NT_F), NT_F, smem, (cudaStream_t)stream>>>(*d);
     g_launches = 1;
@@ -1122,11 +1145,12 @@ int cvxpnpl_b200_assemble(const cvxpnpl_b200_desc* d, double* Q, double* Bmat, v
     if (d->n_pts + d->n_lines <= 0) return fail(-4, "no correspondences");
     if (d->n_pts + d->n_lines >= LARGE_N) {
         // bandwidth-bound regime: chunked streaming reduction (3 operations on the stream)
+        const int chunks = (d->n_pts + d->n_lines + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
+        if (d->batch > 2147483647LL || chunks > 65535)
+            return fail(-8, "large-n assembly: at most 2^31 - 1 problems of at most 65535 x 4096 correspondences per call");
         cudaError_t e0 = cudaMemsetAsync(Q, 0, (size_t)d->batch * 81 * sizeof(double), (cudaStream_t)stream);
         if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
-        const int chunks = (d->n_pts + d->n_lines + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
-        if (d->batch > 65535) return fail(-8, "large-n assembly supports at most 65535 problems per call");
-        accumulate_kernel<<<dim3((unsigned)chunks, (unsigned)d->batch), NT_L, 0, (cudaStream_t)stream>>>(*d, Q);
+        accumulate_kernel<<<dim3((unsigned)d->batch, (unsigned)chunks), NT_L, 0, (cudaStream_t)stream>>>(*d, Q);
         finalize_kernel<<<(unsigned)((d->batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*d, Q, Bmat);
         g_launches = 2;
         cudaError_t e = cudaGetLastError();
@@ -1150,12 +1174,11 @@ int cvxpnpl_b200_solve_sdp(const cvxpnpl_b200_desc* d, const double* Q, void* st
     if (d->workspace_bytes < cvxpnpl_b200_workspace_bytes(d->batch) ||
         (cvxpnpl_b200_workspace_bytes(d->batch) && !d->workspace))
         return fail(-7, "workspace too small");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(solve_sdp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)SMEM_BYTES);
+    {
+        const cudaError_t e = opt_in_once(2, [] {
+            return cudaFuncSetAttribute(solve_sdp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        });
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-        attr_set = true;
     }
     const int64_t slots = device_slots(d->batch);
     const int64_t want = (d->batch + NT - 1) / NT;
@@ -1180,11 +1203,11 @@ int cvxpnpl_b200_extract(const cvxpnpl_b200_desc* d, const double* Z, const doub
     if (!Z || !Q || !Bmat) return fail(-5, "null input pointer");
     if (!d->R || !d->t || !d->n_poses || !d->status) return fail(-6, "null output pointer");
     const size_t smem = (size_t)NT_X * 227 * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        const cudaError_t e = opt_in_once(3, [smem] {
+            return cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-        attr_set = true;
     }
     const int64_t blocks = (d->batch + NT_X - 1) / NT_X;
     const double eps = d->eps > 0 ? d->eps : 1e-9;

@@ -465,7 +465,11 @@ CVX_HD bool pass_dr(const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L, QRT Q
     const double res = dr_step(M, V, L, T, QR, o.alpha, 1.0 / o.sigma, o.rowk, z);
     ++st.it;
 #if defined(CVX_TRACE) && !defined(__CUDA_ARCH__)
-    printf("it %d res %.3e aa_mask %u\n", st.it, sqrt(res), st.aa.mask);
+    {
+        int np_ = 0; double l1 = -1e300, l2 = -1e300, lneg = -1e300;
+        for (int j = 0; j < 10; ++j) { const double l = L[j]; np_ += l > 0; if (l > l1) { l2 = l1; l1 = l; } else if (l > l2) l2 = l; if (l <= 0 && l > lneg) lneg = l; }
+        printf("it %d res %.3e aa_mask %u npos %d l1 %.3e l2 %.3e lneg %.3e\n", st.it, sqrt(res), st.aa.mask, np_, l1, l2, lneg);
+    }
 #endif
     if (!(res > o.eps2)) {  // also leaves on NaN
         st.converged = (res <= o.eps2);
@@ -582,6 +586,54 @@ CVX_HD double dual_objective(Arr<S> V, Arr<S> L, QR qr, double rho, double sigma
     return rho * ((tq + tr9) * (1.0 / 3.0) + sigma * sigma * u99);
 }
 
+// A problem whose assembly is not finite is either non-finite input -- the reference carries the
+// NaNs into SCS and returns the NaN pose (cvxpnpl.py:493-498): ST_NAN -- or finite input with an
+// exactly singular 3x3 system (K, or the normal matrix N'N of degenerate bearings), where the
+// reference's np.linalg.solve raises LinAlgError (cvxpnpl.py:37, 123-125, 548 | 579 | 623):
+// ST_SINGULAR.  Only called for problems that are already known to be non-finite.
+CVX_HD bool normal_system_singular(const Problem& pr)
+{
+    double Kl[9], Ki[9];
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        Kl[i] = pr.K[i];
+        fin = fin && isfinite(Kl[i]);
+    }
+    inv3(Kl, Ki);
+    bool ki_fin = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ki_fin = ki_fin && isfinite(Ki[i]);
+    double W[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < pr.n_pts; ++i) {
+        double p[3];
+        bearing(Ki, pr.pts_2d[2 * i], pr.pts_2d[2 * i + 1], p);
+        fin = fin && isfinite(pr.pts_2d[2 * i]) && isfinite(pr.pts_2d[2 * i + 1]) && isfinite(pr.pts_3d[3 * i]) &&
+              isfinite(pr.pts_3d[3 * i + 1]) && isfinite(pr.pts_3d[3 * i + 2]);
+        const double n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        W[0] += n2 - p[0] * p[0]; W[1] -= p[1] * p[0]; W[2] += n2 - p[1] * p[1];
+        W[3] -= p[2] * p[0]; W[4] -= p[2] * p[1]; W[5] += n2 - p[2] * p[2];
+    }
+    for (int i = 0; i < pr.n_lines; ++i) {
+        double a[3], b[3];
+        bearing(Ki, pr.line_2d[4 * i], pr.line_2d[4 * i + 1], a);
+        bearing(Ki, pr.line_2d[4 * i + 2], pr.line_2d[4 * i + 3], b);
+        for (int e = 0; e < 4; ++e) fin = fin && isfinite(pr.line_2d[4 * i + e]);
+        for (int e = 0; e < 6; ++e) fin = fin && isfinite(pr.line_3d[6 * i + e]);
+        double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        if (!(nn > 0.0)) continue;   // coincident endpoints: NaN normal in the reference, not an exception
+        const double inv = 2.0 / nn;  // both endpoints of the line add n n'
+        W[0] += inv * n[0] * n[0]; W[1] += inv * n[1] * n[0]; W[2] += inv * n[1] * n[1];
+        W[3] += inv * n[2] * n[0]; W[4] += inv * n[2] * n[1]; W[5] += inv * n[2] * n[2];
+    }
+    if (!fin) return false;          // non-finite data: NaN pose, like the reference
+    if (!ki_fin) return true;        // singular K
+    const double det = W[0] * (W[2] * W[5] - W[4] * W[4]) - W[1] * (W[1] * W[5] - W[4] * W[3]) +
+                       W[3] * (W[1] * W[4] - W[2] * W[3]);
+    return isfinite(det) && !isfinite(1.0 / det);
+}
+
 template <int S>
 CVX_HD void write_Z(Arr<S> V, const double lam[10], bool is_nan, double* Zo)
 {
@@ -594,6 +646,20 @@ CVX_HD void write_Z(Arr<S> V, const double lam[10], bool is_nan, double* Zo)
             Zo[r * 10 + c] = s;
             Zo[c * 10 + r] = s;
         }
+}
+
+// result of a problem whose 3x3 system is exactly singular: no pose, ST_SINGULAR (LinAlgError in the scalar API)
+CVX_HD void singular_result(double* R_out, double* t_out, Result& rs)
+{
+    const double qnan = nan("");
+#pragma unroll 4
+    for (int i = 0; i < 36; ++i) R_out[i] = qnan;
+#pragma unroll 4
+    for (int i = 0; i < 12; ++i) t_out[i] = qnan;
+    rs.n_poses = 0;
+    rs.status = ST_SINGULAR;
+    rs.pobj = qnan;
+    rs.dobj = qnan;
 }
 
 template <int S, class QRT>
@@ -612,6 +678,11 @@ CVX_HD void problem_finish(const Problem& pr, const Opts& o, Arr<S> V, Arr<S> M,
     }
     const double dobj = (status != ST_NAN) ? st.dobj : nan("");
     if (Z_out) write_Z(V, lam, status == ST_NAN, Z_out);
+    if (status == ST_NAN && normal_system_singular(pr)) {
+        singular_result(R_out, t_out, rs);
+        rs.iters = st.it;
+        return;
+    }
     // Q and B are re-assembled (cheap) into the now free M / T regions
     Arr<S> Qs = M;
     Arr<S> Bs = T;
@@ -667,6 +738,10 @@ CVX_HD void extract_parked(const Problem& pr, const Opts& o, const double* park,
     const double dobj = park[110];
     int32_t status = (int32_t)park[111];
     if (Z_out) write_Z(V, lam, status == ST_NAN, Z_out);
+    if (status == ST_NAN && normal_system_singular(pr)) {
+        singular_result(R_out, t_out, rs);
+        return;
+    }
     if (status != ST_NAN) assemble(pr.K, pr.pts_2d, pr.pts_3d, pr.n_pts, pr.line_2d, pr.line_3d, pr.n_lines, Qs, Bs);
     double pobj;
     rs.n_poses = extract_poses(V, lam, Qs, Bs, status, dobj, sqrt(o.eps2), R_out, t_out, pobj);

@@ -39,8 +39,11 @@ class HostPipeline:
         with torch.cuda.stream(self.copy_stream):
             if self.free[slot] is not None:
                 self.copy_stream.wait_event(self.free[slot])      # the previous solve on this slot is done
-            if self.buf[slot] is None:
-                self.buf[slot] = {k: torch.empty_like(v, device=self.device) for k, v in host.items() if v is not None}
+            live = {k: v for k, v in host.items() if v is not None}
+            cur = self.buf[slot]
+            if cur is None or cur.keys() != live.keys() or any(cur[k].shape != v.shape for k, v in live.items()):
+                # first use of the slot, or the batch changed shape: (re)allocate the staged buffers
+                self.buf[slot] = {k: torch.empty_like(v, device=self.device) for k, v in live.items()}
             for k, v in host.items():
                 if v is not None:
                     self.buf[slot][k].copy_(v, non_blocking=True)
@@ -63,7 +66,8 @@ class HostPipeline:
         inp = self.buf[slot]
         B = next(iter(inp.values())).shape[0]
         if self.ws is None or self.ws_batch != B:
-            self.ws, self.ws_batch, self.out = Workspace(B, self.device), B, None
+            with torch.cuda.device(self.device):       # the workspace is sized for THIS device's SM count
+                self.ws, self.ws_batch, self.out = Workspace(B, self.device), B, None
             self.host_out = torch.empty((B, RECORD), dtype=torch.float64).pin_memory()
         self.out = solve_batched(self.K, pts_2d=inp.get("pts_2d"), pts_3d=inp.get("pts_3d"), line_2d=inp.get("line_2d"),
                                  line_3d=inp.get("line_3d"), workspace=self.ws, out=self.out, **self.kw)
@@ -97,9 +101,10 @@ class HostStager:
     def solve(self, host: Dict[str, torch.Tensor]) -> BatchedPoses:
         host = {k: v for k, v in host.items() if v is not None and v.shape[1] > 0}
         B = next(iter(host.values())).shape[0]
-        if self.buf is None or next(iter(self.buf.values())).shape[0] != B:
+        if self.buf is None or self.buf.keys() != host.keys() or any(self.buf[k].shape != v.shape for k, v in host.items()):
             self.buf = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
-            self.ws, self.out = Workspace(B, self.device), None
+            with torch.cuda.device(self.device):       # the workspace is sized for THIS device's SM count
+                self.ws, self.out = Workspace(B, self.device), None
         main = torch.cuda.current_stream(self.device)
         bounds = [(c * B) // self.chunks for c in range(self.chunks + 1)]
         events = []

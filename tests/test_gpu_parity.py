@@ -112,34 +112,32 @@ def test_golden_synth(cb, golden, name, n_pts, n_lines):
         assert terr.max() < T_TOL, (key, terr)
 
 
-@pytest.mark.parametrize("n_pts,n_lines,noise", [(8, 4, 1.0), (8, 0, 2.0), (8, 4, 0.0), (6, 0, 1.0), (0, 8, 1.0)])
+@pytest.mark.parametrize("n_pts,n_lines,noise", [(8, 4, 1.0), (8, 0, 2.0), (8, 4, 0.0), (6, 0, 1.0), (0, 8, 1.0),
+                                                 (0, 6, 1.0), (8, 4, 2.0)])
 def test_parity_vs_oracle_seeded(cb, n_pts, n_lines, noise):
-    """Same seeded inputs through the CUDA path and the CPU oracle (restated SCS)."""
+    """Same seeded inputs through the CUDA path and the CPU oracle (restated SCS).  EVERY problem of
+    the batch is compared -- a problem that stops at the reference's iteration cap (status
+    MAX_ITERS, SCS "solved_inaccurate") is held to the same tolerance, not dropped."""
     from cvxpnpl_b200 import synth
     from oracle import cvxpnpl_oracle as orc
     from oracle import kkt
-    B = 48
+    B = 400
     d = synth.make_batch(B, n_pts, n_lines, noise=noise, seed=11)
     res = _solve(cb, d, n_pts, n_lines, return_Z=True)
     R, t, Z = res.R.cpu().numpy(), res.t.cpu().numpy(), res.Z.cpu().numpy()
     st = res.status.cpu().numpy() & 0xFF
-    # a few percent of small-n problems are slow for plain ADMM and stop at the
-    # reference's own iteration cap (2500) with status MAX_ITERS, like SCS's
-    # "solved_inaccurate"; parity is asserted on the converged ones.
-    assert np.isin(st, (0, 1)).all() and (st == 0).mean() >= 0.9, st
-    worst = [0.0, 0.0]
+    assert np.isin(st, (0, 1)).all(), np.bincount(st)
+    rot, tr = np.zeros(B), np.zeros(B)
     for i in range(B):
-        if st[i] != 0:
-            continue
         poses, aux = _oracle_call(orc, d, i, n_pts, n_lines, max_iters=200000, return_aux=True)
-        assert len(poses) == int(res.n_poses[i]) == 1
+        assert len(poses) == int(res.n_poses[i]) == 1, (i, len(poses), int(res.n_poses[i]), st[i])
         Ro, to = poses[0]
-        worst[0] = max(worst[0], float(synth.rotation_angle(Ro, R[i, 0])))
-        worst[1] = max(worst[1], float(np.linalg.norm(to - t[i, 0]) / np.linalg.norm(to)))
+        rot[i] = synth.rotation_angle(Ro, R[i, 0])
+        tr[i] = np.linalg.norm(to - t[i, 0]) / np.linalg.norm(to)
         # solver-independent certificate on the CUDA Z, using the oracle's multipliers
         cert = kkt.certificate(aux["Q"], Z[i], aux["info"]["y"])
-        assert cert["eq_res"] < 1e-7 and cert["psd_res"] < 1e-9 and cert["gap"] < 1e-7, cert
-    assert worst[0] < ROT_TOL and worst[1] < T_TOL, worst
+        assert cert["eq_res"] < 1e-7 and cert["psd_res"] < 1e-9 and cert["gap"] < 1e-7, (i, st[i], cert)
+    assert rot.max() < ROT_TOL and tr.max() < T_TOL, (rot.max(), tr.max(), int(rot.argmax()), np.bincount(st))
 
 
 def test_full_size_properties(cb):
@@ -195,7 +193,8 @@ def test_edge_cases(cb):
 @pytest.mark.parametrize("name", ["pts4", "pts3", "lines3", "lines4", "p2l1", "coplanar8"])
 def test_extraction_degenerate(cb, golden, name):
     """Multi-solution extraction (cvxpnpl.py:221-343, 156-218) replayed on the Z the
-    reference saw (golden), compared with the reference's candidate poses as sets."""
+    reference saw (golden), compared with the reference's candidate poses as sets; where the
+    reference raised LinAlgError the CUDA path must report ST_SINGULAR."""
     g = golden["degenerate"]
     Z, Q, Bm = g[name + "_Z"], g[name + "_AtA"], g[name + "_B"]
     res = cb.extract_batched(Z, Q, Bm)
@@ -204,7 +203,8 @@ def test_extraction_degenerate(cb, golden, name):
     npo, st = res.n_poses.cpu().numpy(), res.status.cpu().numpy()
     for i in range(len(Z)):
         if not g[name + "_ok"][i]:
-            continue  # LinAlgError in the reference: an exactly singular system; no set to compare
+            assert st[i] & 0xFF == 3 and npo[i] == 0, (name, i, st[i], npo[i])   # ST_SINGULAR <-> LinAlgError
+            continue
         n = int(g[name + "_n"][i])
         assert npo[i] == n, (name, i, npo[i], n, st[i])
         got = np.concatenate([R[i, :n].reshape(n, 9), t[i, :n]], axis=1)
@@ -213,6 +213,88 @@ def test_extraction_degenerate(cb, golden, name):
         # see tests/test_oracle.py::test_degenerate_extraction for the tolerance
         assert dist[(n - 1) // 2] < 1e-6, (name, i, dist)
         assert np.all(dist[: max(n - 1, 1)] < 1e-4), (name, i, dist)
+
+
+@pytest.mark.parametrize("name", ["pts4", "pts3", "lines3", "lines4", "p2l1", "coplanar8", "pts5"])
+def test_extraction_degenerate_big(cb, name):
+    """tests/golden/degenerate_big.npz (40 problems per family, verbatim reference): the reference's
+    exceptions (LinAlgError at cvxpnpl.py:165 / 212 / 510) map to ST_SINGULAR, the number of candidates
+    is the reference's, and EVERY candidate the reference itself reproduces under a 1e-14 perturbation
+    of Z is matched to 1e-6 (the others sit on near-double roots of the resultant quartic and are
+    only counted; see tests/degenerate_util.py)."""
+    import os
+    from tests import degenerate_util as du
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "degenerate_big.npz"))
+    res = cb.extract_batched(g[name + "_Z"], g[name + "_AtA"], g[name + "_B"])
+    torch.cuda.synchronize()
+    R, t = res.R.cpu().numpy(), res.t.cpu().numpy()
+    npo, st = res.n_poses.cpu().numpy(), res.status.cpu().numpy() & 0xFF
+    total = stable = 0
+    for i in range(len(npo)):
+        if g[name + "_err"][i] == 1:
+            assert st[i] == 3 and npo[i] == 0, (name, i, st[i], npo[i])
+            continue
+        n = int(g[name + "_n"][i])
+        assert npo[i] == n and st[i] == 0, (name, i, npo[i], n, st[i])
+        exp, got = du.flat(g[name + "_R"][i], g[name + "_t"][i], n), du.flat(R[i], t[i], n)
+        m = du.stable_mask(exp, g[name + "_Rp"][i], g[name + "_tp"][i], g[name + "_np"][i])
+        total, stable = total + n, stable + int(m.sum())
+        assert du.compare(got, exp, m) < 1e-6, (name, i, du.compare(got, exp, m))
+    assert stable >= 0.85 * total, (name, stable, total)     # the filter must not hollow the test out
+
+
+@pytest.mark.parametrize("n_pts,n_lines,coplanar", [(3, 0, False), (4, 0, False), (0, 3, False), (2, 1, False),
+                                                    (0, 4, False), (8, 0, True)])
+def test_degenerate_candidates_vs_oracle_same_Z(cb, n_pts, n_lines, coplanar):
+    """BASELINE config 5 on 600 FRESH problems per family: the CUDA path's candidate poses against the
+    oracle's extraction (pinned to the verbatim reference by tests/test_oracle.py) fed the SAME Z the
+    CUDA solver returned, compared as sets.  Candidates the oracle itself does not reproduce under a
+    1e-14 perturbation of Z (near-double quartic roots) are excluded and counted."""
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    from tests import degenerate_util as du
+    B = 600
+    d = synth.make_batch(B, n_pts, n_lines, noise=0.0, seed=19, coplanar=coplanar)
+    res = _solve(cb, d, n_pts, n_lines, return_Z=True)
+    R, t, Z = res.R.cpu().numpy(), res.t.cpu().numpy(), res.Z.cpu().numpy()
+    npo, st = res.n_poses.cpu().numpy(), res.status.cpu().numpy() & 0xFF
+    rng = np.random.default_rng(3)
+    total = stable = compared = errors = borderline = 0
+    for i in range(B):
+        C, N = orc._stack(d["pts_2d"][i] if n_pts else None, d["pts_3d"][i] if n_pts else None,
+                          d["line_2d"][i] if n_lines else None, d["line_3d"][i] if n_lines else None, d["K"])
+        A, Bm = orc.reduce_translation(C, N)
+        lam = np.linalg.eigvalsh(Z[i])
+        if np.any(np.abs(lam - 1e-3) < 1e-6):
+            borderline += 1                     # an eigenvalue sits ON the rank threshold (cvxpnpl.py:502)
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                poses = orc.extract(Z[i], A, Bm)
+            except np.linalg.LinAlgError:
+                assert st[i] == 3 and npo[i] == 0, (i, st[i], npo[i])
+                errors += 1
+                continue
+            pert = []
+            for _ in range(3):
+                try:
+                    pert.append(orc.extract(Z[i] * (1.0 + 1e-14 * rng.standard_normal((10, 10))), A, Bm))
+                except np.linalg.LinAlgError:
+                    pert.append([])
+        n = len(poses)
+        assert npo[i] == n and st[i] in (0, 1), (i, npo[i], n, st[i])
+        exp = np.array([np.concatenate([Rr.ravel(), tt]) for Rr, tt in poses])
+        got = du.flat(R[i], t[i], n)
+        Rp = np.full((3, 4, 3, 3), np.nan)
+        tp = np.full((3, 4, 3), np.nan)
+        for k, pp in enumerate(pert):
+            for c, (Rr, tt) in enumerate(pp):
+                Rp[k, c], tp[k, c] = Rr, tt
+        m = du.stable_mask(exp, Rp, tp, np.array([len(pp) for pp in pert]))
+        total, stable, compared = total + n, stable + int(m.sum()), compared + 1
+        assert du.compare(got, exp, m) < 1e-6, (i, n, du.compare(got, exp, m))
+    assert compared + errors >= 0.98 * B and stable >= 0.8 * total, (compared, errors, borderline, stable, total)
 
 
 @pytest.mark.parametrize("n_pts,n_lines,coplanar,min_found", [

@@ -139,3 +139,48 @@ def test_host_fp32_first_phase(n_pts, n_lines):
         Z = m["Z"][i]
         assert abs(Z[9, 9] - 1.0) < 1e-8 and np.linalg.eigvalsh(Z).min() > -1e-9
         assert abs(np.trace(Z[:9, :9]) - 3.0) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["pts4", "pts3", "lines3", "lines4", "p2l1", "coplanar8", "pts5"])
+def test_host_extraction_degenerate_big(name):
+    """The device extraction routines (host build) on tests/golden/degenerate_big.npz: ST_SINGULAR exactly
+    where the verbatim reference raised LinAlgError (cvxpnpl.py:165 / 212 / 510), the reference's number of
+    candidates, and every reproducible candidate (tests/degenerate_util.py) to 1e-6."""
+    import os
+    from tests import degenerate_util as du
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "degenerate_big.npz"))
+    total = stable = 0
+    for i in range(len(g[name + "_err"])):
+        n, R, t, st = harness.extract(g[name + "_Z"][i], g[name + "_AtA"][i], g[name + "_B"][i])
+        if g[name + "_err"][i] == 1:
+            assert st & 0xFF == 3 and n == 0, (name, i, st, n)
+            continue
+        ne = int(g[name + "_n"][i])
+        assert n == ne and st & 0xFF == 0, (name, i, n, ne, st)
+        exp, got = du.flat(g[name + "_R"][i], g[name + "_t"][i], ne), du.flat(R, t, n)
+        m = du.stable_mask(exp, g[name + "_Rp"][i], g[name + "_tp"][i], g[name + "_np"][i])
+        total, stable = total + ne, stable + int(m.sum())
+        assert du.compare(got, exp, m) < 1e-6, (name, i, du.compare(got, exp, m))
+    assert stable >= 0.85 * total
+
+
+def test_host_quartic_matches_np_roots():
+    """quartic_real_parts (Ferrari start + Aberth-Ehrlich polish) against np.real(np.roots(..)) (cvxpnpl.py:185-186),
+    including the badly scaled quartics the rank-4 branch produces (one root at 1e5, three near 1e-2) and
+    complex pairs."""
+    rng = np.random.default_rng(0)
+    cases = [np.array([2.13399037e-30, 3.19277247e-27, -2.21505703e-25, 8.37712288e-26, 5.51503240e-31]),
+             np.array([3.89663680e-18, -2.85182644e-14, -2.32927774e-11, -1.97020291e-09, 2.67766077e-14])]
+    for k in range(600):
+        if k % 3 == 0:
+            cases.append(rng.standard_normal(5))
+        elif k % 3 == 1:
+            cases.append(np.poly(rng.standard_normal(4) * 10.0 ** rng.integers(-3, 4, 4))[::-1] * rng.standard_normal())
+        else:
+            a = rng.standard_normal() + 1j * rng.standard_normal()
+            cases.append(np.real(np.poly([a, np.conj(a), 100 * rng.standard_normal(), 1e-3 * rng.standard_normal()]))[::-1])
+    for c in cases:
+        ref = np.sort(np.real(np.roots(c[::-1])))
+        got = np.sort(harness.quartic(c))
+        assert len(ref) == len(got)
+        assert np.all(np.abs(ref - got) <= 1e-7 * np.maximum(np.abs(ref), 1e-9)), (c, ref, got)

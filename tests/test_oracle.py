@@ -126,6 +126,35 @@ def test_degenerate_extraction(golden, name):
         assert np.all(dist[: max(n - 1, 1)] < 1e-4)
 
 
+@pytest.mark.parametrize("name", ["pts4", "pts3", "lines3", "lines4", "p2l1", "coplanar8", "pts5"])
+def test_degenerate_extraction_big(name):
+    """tests/golden/degenerate_big.npz (generator make_degenerate_big.py, verbatim reference): 40 problems
+    per family.  The oracle raises LinAlgError exactly where the reference did, returns the same number
+    of candidates, and matches every candidate the reference itself reproduces under a 1e-14
+    perturbation of Z (tests/degenerate_util.py) to 1e-6."""
+    import os
+    from tests import degenerate_util as du
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "degenerate_big.npz"))
+    total = stable = 0
+    for i in range(len(g[name + "_err"])):
+        if g[name + "_err"][i] == 1:
+            with pytest.raises(np.linalg.LinAlgError), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                orc.extract(g[name + "_Z"][i], np.zeros((1, 9)), g[name + "_B"][i])
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            poses = orc.extract(g[name + "_Z"][i], np.zeros((1, 9)), g[name + "_B"][i])
+        n = int(g[name + "_n"][i])
+        assert len(poses) == n
+        got = np.array([np.concatenate([R.ravel(), t]) for R, t in poses])
+        exp = du.flat(g[name + "_R"][i], g[name + "_t"][i], n)
+        m = du.stable_mask(exp, g[name + "_Rp"][i], g[name + "_tp"][i], g[name + "_np"][i])
+        total, stable = total + n, stable + int(m.sum())
+        assert du.compare(got, exp, m) < 1e-6, (name, i)
+    assert stable >= 0.85 * total, (name, stable, total)
+
+
 def test_rc_variant_against_reference(golden):
     """benchmarks/toolkit/methods/rc.py: static data and poses of the verbatim reference."""
     g = golden["rc"]
