@@ -50,6 +50,7 @@ class Desc(ctypes.Structure):
         ("timing", ctypes.c_int32),
         ("skip_prepass", ctypes.c_int32),
         ("reserved3", ctypes.c_int32),
+        ("record", ctypes.c_void_p),
     ]
 
 

@@ -31,6 +31,7 @@ class BatchedPoses:
     obj: Optional[torch.Tensor] = None  # [B, 2] (r'Qr of candidate 0, dual objective)
     Z: Optional[torch.Tensor] = None    # [B, 10, 10]
     launches: int = 0
+    record: Optional[torch.Tensor] = None   # [B, 15] packed (R0 | t0 | n_poses | status | iters), see distributed.RECORD
 
 
 def _require_cuda():
@@ -66,7 +67,7 @@ class Workspace:
 def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1e-9, max_iters=2500,
                   sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, variant="full", return_Z=False, return_obj=True, workspace=None,
                   out: Optional[BatchedPoses] = None, device=None, handoff=0, admm_dtype="f64",
-                  fp32_iters=400, timing=False, _prepass_hook=None) -> BatchedPoses:
+                  fp32_iters=400, timing=False, _prepass_hook=None, record=None) -> BatchedPoses:
     """Solve B problems.  pts_2d [B,n,2], pts_3d [B,n,3], line_2d [B,m,2,2],
     line_3d [B,m,2,3], K [3,3] or [B,3,3]; any of the point / line pairs may be
     omitted (PnP / PnL / PnPL: cvxpnpl.py:523-627).  variant="rc" solves the ablation
@@ -75,7 +76,9 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
     moves to the warp-per-problem straggler kernel (0 = default, < 0 = never).
     admm_dtype="f32": "fp32 ADMM + fp64 extraction" (BASELINE.json configs[3]) -- the
     iterations that bring a problem into the linear tail run in FP32 (at most
-    fp32_iters), the FP64 solver finishes to `eps`."""
+    fp32_iters), the FP64 solver finishes to `eps`.
+    record: optional [B,15] float64 CUDA tensor (may be a slice of an all-gather buffer) that the finish
+    kernel fills with the packed row (R0 | t0 | n_poses | status | iters) of every problem."""
     _require_cuda()
     lib = _lib.load()
     if device is None:
@@ -127,6 +130,7 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         # Options that only exist on the fused path are refused, never silently dropped.
         unsupported = [name for name, given in (("admm_dtype='f32'", admm_dtype != "f64"), ("out", out is not None),
                                                 ("handoff", handoff != 0), ("timing", bool(timing)),
+                                                ("record", record is not None),
                                                 ("_prepass_hook", _prepass_hook is not None)) if given]
         if unsupported:
             raise NotImplementedError(f"{', '.join(unsupported)}: not available with >= {LARGE_N} correspondences per "
@@ -181,6 +185,12 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.timing = int(bool(timing))
         d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
+        if record is not None:
+            if (not record.is_cuda or record.dtype != torch.float64 or tuple(record.shape) != (B, 15)
+                    or not record.is_contiguous()):
+                raise ValueError("record must be a contiguous [B,15] float64 CUDA tensor")
+            out.record = record
+        d.record = _ptr(record)
         d.workspace, d.workspace_bytes = _ptr(workspace.buf), workspace.nbytes
         stream = torch.cuda.current_stream(device).cuda_stream
         extra = 0

@@ -527,6 +527,19 @@ __global__ void __launch_bounds__(NT_F) finish_kernel(cvxpnpl_b200_desc d, Opts 
         d.obj[2 * b] = rs.pobj;
         d.obj[2 * b + 1] = rs.dobj;
     }
+    if (d.record) {
+        // packed [R0 | t0 | n_poses | status | iters] row: what leaves the GPU (all-gather / D2H)
+        double* rec = d.record + b * CVXPNPL_RECORD;
+        const double* R0 = d.R + b * 36;
+        const double* t0 = d.t + b * 12;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) rec[i] = R0[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rec[9 + i] = t0[i];
+        rec[12] = (double)rs.n_poses;
+        rec[13] = (double)rs.status;
+        rec[14] = (double)d.iters[b];
+    }
 }
 
 // ---------------------------------------------------------------------------------

@@ -43,33 +43,71 @@ def unpack_record(rec: torch.Tensor):
 def gather_records(local: torch.Tensor, total: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     """All-gather ragged shards (sizes given by shard_bounds) into [total, RECORD].
     Shards are padded to the largest shard so a single all_gather_into_tensor
-    (one NCCL call) does the job."""
+    (one NCCL call) does the job.  (Convenience form that copies; RecordGatherer is the
+    copy-free one the bench and solve_sharded use.)"""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
-    sizes = [shard_bounds(total, r, world) for r in range(world)]
-    width = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((width, local.shape[1]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    out = torch.empty((world * width, local.shape[1]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad, group=group)
-    return torch.cat([out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    g = RecordGatherer(total, local.device, group=group)
+    g.slot[: local.shape[0]].copy_(local)
+    return g.gather()
 
 
-def solve_sharded(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, group=None, solver=None, **kw):
+class RecordGatherer:
+    """The path's one collective without staging copies: a persistent [world * width, RECORD] buffer
+    whose slice `slot` ([width, RECORD], this rank's place) is handed to the solver as its packed-record
+    output (`solve_batched(record=gatherer.local)`), so the finish kernel writes the rows where the
+    all-gather reads them and `all_gather_into_tensor` runs IN PLACE (input = the rank's slice of the
+    output: no pad, no concatenate).  width = the largest shard; with a batch that does not divide evenly
+    the trailing row of the smaller shards is padding and `gather()` drops it."""
+
+    def __init__(self, total: int, device, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.total = total
+        self.bounds = [shard_bounds(total, r, self.world) for r in range(self.world)]
+        self.width = max(hi - lo for lo, hi in self.bounds) if total else 0
+        self.buf = torch.zeros((self.world * self.width, RECORD), dtype=torch.float64, device=device)
+        self.slot = self.buf[self.rank * self.width: (self.rank + 1) * self.width]
+        lo, hi = self.bounds[self.rank]
+        self.local = self.slot[: hi - lo]      # [own shard, RECORD]: pass this as `record=`
+        self.even = all(hi - lo == self.width for lo, hi in self.bounds)
+
+    def gather(self) -> torch.Tensor:
+        """-> [total, RECORD] on every rank (a view of the buffer when the shards are equal)."""
+        if self.world > 1 and self.width:
+            dist.all_gather_into_tensor(self.buf, self.slot, group=self.group)
+        if self.even:
+            return self.buf
+        return torch.cat([self.buf[r * self.width: r * self.width + (hi - lo)] for r, (lo, hi) in enumerate(self.bounds)],
+                         dim=0)
+
+
+def solve_sharded(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, group=None, solver=None, gatherer=None,
+                  **kw):
     """Every rank passes the FULL batch (host or device tensors); each solves its own
-    contiguous shard on its GPU and the poses are all-gathered.  Returns
-    (R [B,3,3], t [B,3], n_poses, status, iters) of candidate 0 on every rank.
-    `solver` defaults to cvxpnpl_b200.solve_batched (injectable for CPU tests)."""
-    if solver is None:
-        from .batched import solve_batched as solver
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    contiguous shard on its GPU and the poses are all-gathered (strong scaling: SURVEY 8e,
+    "rank g gets problems [g B/G, (g+1) B/G)").  Returns (R [B,3,3], t [B,3], n_poses, status,
+    iters) of candidate 0 on every rank.  `solver` defaults to cvxpnpl_b200.solve_batched
+    (injectable for CPU tests); `gatherer` (a RecordGatherer for this batch size) can be kept
+    across calls so nothing is allocated per step."""
     ref = pts_2d if pts_2d is not None else line_2d
     total = ref.shape[0]
-    lo, hi = shard_bounds(total, rank, world)
+    real = solver is None
+    if real:
+        from .batched import solve_batched as solver
+    if gatherer is None:
+        dev = ref.device if (ref.is_cuda or not real) else torch.device("cuda", torch.cuda.current_device())
+        gatherer = RecordGatherer(total, dev, group=group)
+    lo, hi = gatherer.bounds[gatherer.rank]
     sl = lambda x: None if x is None else x[lo:hi]  # noqa: E731
     Kl = K[lo:hi] if (hasattr(K, "dim") and K.dim() == 3) else K
-    res = solver(Kl, pts_2d=sl(pts_2d), pts_3d=sl(pts_3d), line_2d=sl(line_2d), line_3d=sl(line_3d), **kw)
-    rec = pack_record(res.R[:, 0], res.t[:, 0], res.n_poses, res.status, res.iters)
-    return unpack_record(gather_records(rec, total, group))
+    if real:
+        # the finish kernel writes the packed rows straight into this rank's slice of the gather buffer
+        solver(Kl, pts_2d=sl(pts_2d), pts_3d=sl(pts_3d), line_2d=sl(line_2d), line_3d=sl(line_3d),
+               record=gatherer.local, **kw)
+    else:
+        res = solver(Kl, pts_2d=sl(pts_2d), pts_3d=sl(pts_3d), line_2d=sl(line_2d), line_3d=sl(line_3d), **kw)
+        gatherer.local.copy_(pack_record(res.R[:, 0], res.t[:, 0], res.n_poses, res.status, res.iters))
+    return unpack_record(gatherer.gather())

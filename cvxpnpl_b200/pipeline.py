@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .batched import BatchedPoses, Workspace, solve_batched
-from .distributed import RECORD, pack_record
+from .distributed import RECORD
 
 _KEYS = ("pts_2d", "pts_3d", "line_2d", "line_3d")
 
@@ -68,14 +68,15 @@ class HostPipeline:
         if self.ws is None or self.ws_batch != B:
             with torch.cuda.device(self.device):       # the workspace is sized for THIS device's SM count
                 self.ws, self.ws_batch, self.out = Workspace(B, self.device), B, None
+            self.rec = torch.empty((B, RECORD), dtype=torch.float64, device=self.device)
             self.host_out = torch.empty((B, RECORD), dtype=torch.float64).pin_memory()
+        # the finish kernel writes the packed [B,15] rows itself (desc.record): no packing pass
         self.out = solve_batched(self.K, pts_2d=inp.get("pts_2d"), pts_3d=inp.get("pts_3d"), line_2d=inp.get("line_2d"),
-                                 line_3d=inp.get("line_3d"), workspace=self.ws, out=self.out, **self.kw)
+                                 line_3d=inp.get("line_3d"), workspace=self.ws, out=self.out, record=self.rec, **self.kw)
         ev = torch.cuda.Event()
         ev.record(main)
         self.free[slot] = ev
-        o = self.out
-        self.host_out.copy_(pack_record(o.R[:, 0], o.t[:, 0], o.n_poses, o.status, o.iters), non_blocking=True)
+        self.host_out.copy_(self.rec, non_blocking=True)
         self.cur = 1 - slot
         return self.host_out
 
@@ -98,7 +99,8 @@ class HostStager:
         self.out = None
         self.done = None     # event: the previous solve no longer reads the input buffers
 
-    def solve(self, host: Dict[str, torch.Tensor]) -> BatchedPoses:
+    def solve(self, host: Dict[str, torch.Tensor], record=None) -> BatchedPoses:
+        """`record`: optional [B,15] CUDA tensor for the packed rows (see solve_batched)."""
         host = {k: v for k, v in host.items() if v is not None and v.shape[1] > 0}
         B = next(iter(host.values())).shape[0]
         if self.buf is None or self.buf.keys() != host.keys() or any(self.buf[k].shape != v.shape for k, v in host.items()):
@@ -132,7 +134,7 @@ class HostStager:
 
         self.out = solve_batched(self.K, pts_2d=self.buf.get("pts_2d"), pts_3d=self.buf.get("pts_3d"),
                                  line_2d=self.buf.get("line_2d"), line_3d=self.buf.get("line_3d"), workspace=self.ws,
-                                 out=self.out, _prepass_hook=hook, **self.kw)
+                                 out=self.out, _prepass_hook=hook, record=record, **self.kw)
         self.done = torch.cuda.Event()
         self.done.record(main)
         return self.out

@@ -88,7 +88,13 @@ typedef struct cvxpnpl_b200_desc {
     int32_t timing;         /* != 0: record CUDA events between the kernels of `solve` (cvxpnpl_b200_kernel_times) */
     int32_t skip_prepass;   /* != 0: the pre-pass of every problem has been run by cvxpnpl_b200_prepass already */
     int32_t reserved3;
+    /* ---- packed output (optional) ---- */
+    double* record;         /* optional [B, 15]: R of candidate 0 (9, row-major) | t (3) | n_poses | status | iters,
+                               written by the finish kernel next to R / t: the row a multi-GPU caller all-gathers
+                               (the path's only collective) or copies back to the host, without a packing pass */
 } cvxpnpl_b200_desc;
+
+#define CVXPNPL_RECORD 15
 
 /* library version string, e.g. "cvxpnpl_b200 0.1.0 (sm_100a)" */
 const char* cvxpnpl_b200_version(void);

@@ -1,4 +1,6 @@
-"""Order-free comparison of candidate-pose sets with the reference's (tests/golden/degenerate_big.npz).
+"""oracle/candidate_sets.py -- TEST INFRASTRUCTURE (checker), not product code.
+
+Order-free comparison of candidate-pose sets with the reference's (tests/golden/degenerate_big.npz).
 
 The rank-4 recovery (cvxpnpl.py:156-218) is ill conditioned at near-double roots of its
 resultant quartic: the reference itself does not reproduce those candidates when Z changes in

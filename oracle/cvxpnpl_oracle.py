@@ -319,11 +319,13 @@ def constraint_ortho_det(vecs, rank):
 # ----------------------------------------------------------------------------
 
 
-def solve_sdp(Q, eps=1e-9, max_iters=2500, variant="full"):
+def solve_sdp(Q, eps=1e-9, max_iters=2500, variant="full", eps_rel=0.0):
     """cvxpnpl.py:478-492 (variant "full") or rc.py:86-96 (variant "rc") with the scs
-    call replaced by oracle/scs_port."""
+    call replaced by oracle/scs_port.  eps_rel = 0 solves to the absolute tolerance the
+    reference asks for; eps_rel = 1e-4 is what real SCS 3.x would add by default (the reference
+    leaves it untouched, cvxpnpl.py:17)."""
     A, b = (_A, _b) if variant == "full" else (_A_rc, _b_rc)
-    res = scs_port.solve(A, b, vech10(Q, 2.0), eps_abs=eps, max_iters=max_iters)
+    res = scs_port.solve(A, b, vech10(Q, 2.0), eps_abs=eps, eps_rel=eps_rel, max_iters=max_iters)
     info = dict(res["info"])
     info["y"] = res["y"]
     return vech10_inv(res["x"]), info
@@ -352,12 +354,12 @@ def extract(Z, A, B, dobj=None, eps=1e-9):
     return list(zip(Rt.transpose(0, 2, 1), t))
 
 
-def solve_relaxation(A, B, eps=1e-9, max_iters=2500, return_aux=False, variant="full"):
+def solve_relaxation(A, B, eps=1e-9, max_iters=2500, return_aux=False, variant="full", eps_rel=0.0):
     """cvxpnpl.py:454-520; variant "rc" = rc.py:65-122 (same extraction, no
     optimality warning)."""
     Q = np.zeros((10, 10))
     Q[:9, :9] = A.T @ A
-    Z, info = solve_sdp(Q, eps, max_iters, variant)
+    Z, info = solve_sdp(Q, eps, max_iters, variant, eps_rel)
     poses = extract(Z, A, B, info["dobj"] if variant == "full" else None, eps)
     if return_aux:
         return poses, {"Z": Z, "Q": Q, "info": info}

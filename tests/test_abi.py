@@ -31,8 +31,8 @@ def test_desc_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"\b([A-Za-z_0-9]+);", body)
     assert names == [f[0] for f in _lib.Desc._fields_]
-    # 1 int64 + 4 int32 + 5 ptr + eps + 4 int32 + 3 double + 7 ptr + ptr + size_t + 4 int32
-    assert ctypes.sizeof(_lib.Desc) == 8 + 16 + 40 + 8 + 16 + 24 + 56 + 8 + 8 + 16
+    # 1 int64 + 4 int32 + 5 ptr + eps + 4 int32 + 3 double + 7 ptr + ptr + size_t + 4 int32 + record ptr
+    assert ctypes.sizeof(_lib.Desc) == 8 + 16 + 40 + 8 + 16 + 24 + 56 + 8 + 8 + 16 + 8
 
 
 def test_no_cpu_fallback():

@@ -221,9 +221,9 @@ def test_extraction_degenerate_big(cb, name):
     exceptions (LinAlgError at cvxpnpl.py:165 / 212 / 510) map to ST_SINGULAR, the number of candidates
     is the reference's, and EVERY candidate the reference itself reproduces under a 1e-14 perturbation
     of Z is matched to 1e-6 (the others sit on near-double roots of the resultant quartic and are
-    only counted; see tests/degenerate_util.py)."""
+    only counted; see oracle/candidate_sets.py)."""
     import os
-    from tests import degenerate_util as du
+    from oracle import candidate_sets as du
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "degenerate_big.npz"))
     res = cb.extract_batched(g[name + "_Z"], g[name + "_AtA"], g[name + "_B"])
     torch.cuda.synchronize()
@@ -252,7 +252,7 @@ def test_degenerate_candidates_vs_oracle_same_Z(cb, n_pts, n_lines, coplanar):
     1e-14 perturbation of Z (near-double quartic roots) are excluded and counted."""
     from cvxpnpl_b200 import synth
     from oracle import cvxpnpl_oracle as orc
-    from tests import degenerate_util as du
+    from oracle import candidate_sets as du
     B = 600
     d = synth.make_batch(B, n_pts, n_lines, noise=0.0, seed=19, coplanar=coplanar)
     res = _solve(cb, d, n_pts, n_lines, return_Z=True)
@@ -619,3 +619,185 @@ def test_host_stager_matches_direct_solve(cb):
         assert float((res.t[:, 0] - ref.t[:, 0]).abs().cpu()[ok].max()) < 1e-7
         n_slices = len({(c * B) // 4 for c in range(5)}) - 1     # non-empty slices
         assert res.launches == ref.launches + n_slices - 1        # one pre-pass launch per slice instead of one
+
+
+def test_record_output_matches_fields(cb):
+    """desc.record: the packed [B,15] row the finish kernel writes (R0 | t0 | n_poses | status | iters) equals the
+    separately written outputs (what pack_record builds from them)."""
+    from cvxpnpl_b200 import synth
+    from cvxpnpl_b200.distributed import pack_record
+    d = synth.make_batch(5000, 8, 4, noise=1.0, seed=8)
+    d["pts_2d"][7, 0, 0] = np.nan            # one NaN problem: NaN pose, status 2
+    rec = torch.empty((5000, 15), dtype=torch.float64, device="cuda")
+    res = _solve(cb, d, 8, 4, record=rec)
+    ref = pack_record(res.R[:, 0], res.t[:, 0], res.n_poses, res.status, res.iters)
+    assert torch.equal(torch.nan_to_num(rec, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    assert int(rec[7, 13]) & 0xFF == 2 and bool(torch.isnan(rec[7, :12]).all())
+
+
+def test_singular_normal_system_raises_linalgerror(cb):
+    """cvxpnpl.py:548 / 579 / 623: np.linalg.solve(N'N, N'C) raises LinAlgError on an exactly singular 3x3
+    normal matrix (all bearings identical: here every pixel is the principal point of K = I, so
+    N'N = n diag(1,1,0)).  Batch API: ST_SINGULAR, no pose; scalar API: the exception.  Non-finite input
+    stays the NaN pose (cvxpnpl.py:493-498)."""
+    from cvxpnpl_b200 import synth
+    d = synth.make_batch(40, 8, 0, noise=1.0, seed=4)
+    d["K"] = np.eye(3)
+    d["pts_2d"][3] = 0.0
+    d["pts_2d"][5, 1, 1] = np.inf
+    res = _solve(cb, d, 8, 0)
+    st, n = res.status.cpu().numpy() & 0xFF, res.n_poses.cpu().numpy()
+    assert st[3] == 3 and n[3] == 0 and bool(torch.isnan(res.R[3]).all())
+    assert st[5] == 2 and n[5] == 1
+    with pytest.raises(np.linalg.LinAlgError):
+        cb.pnp(d["pts_2d"][3], d["pts_3d"][3], d["K"])
+    # the oracle (restated reference) raises on the same input
+    from oracle import cvxpnpl_oracle as orc
+    with pytest.raises(np.linalg.LinAlgError):
+        orc.pnp(d["pts_2d"][3], d["pts_3d"][3], d["K"])
+
+
+def test_rc_variant_lines_and_large_n(cb):
+    """benchmarks/toolkit/methods/pnl.py:11-34, pnpl.py:12-46 (rc for lines / points + lines) against the
+    oracle's rc variant; and variant="rc" on the large-n (stage-kernel) path, which used to drop it."""
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    d = synth.make_batch(12, 6, 5, noise=1.0, seed=61)
+    for i in range(4):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            A, Bm = orc.reduce_translation(*orc._stack(None, None, d["line_2d"][i], d["line_3d"][i], d["K"]))
+            exp = orc.solve_relaxation(A, Bm, max_iters=200000, variant="rc")
+            got = cb.rc_pnl(d["line_2d"][i], d["line_3d"][i], d["K"])
+            assert len(got) == len(exp) == 1 and synth.rotation_angle(exp[0][0], got[0][0]) < ROT_TOL
+            A, Bm = orc.reduce_translation(*orc._stack(d["pts_2d"][i], d["pts_3d"][i], d["line_2d"][i], d["line_3d"][i], d["K"]))
+            exp = orc.solve_relaxation(A, Bm, max_iters=200000, variant="rc")
+            got = cb.rc_pnpl(d["pts_2d"][i], d["line_2d"][i], d["pts_3d"][i], d["line_3d"][i], d["K"])
+            assert len(got) == len(exp) == 1 and synth.rotation_angle(exp[0][0], got[0][0]) < ROT_TOL
+            assert np.linalg.norm(exp[0][1] - got[0][1]) / np.linalg.norm(exp[0][1]) < T_TOL
+    # large n: the rc and the full SDP have different optima on noisy data -> the variant must reach the stage kernel
+    dl = synth.make_batch(6, 300, 0, noise=2.0, seed=62)
+    full = _solve(cb, dl, 300, 0)
+    rc = _solve(cb, dl, 300, 0, variant="rc")
+    small = {k: (v[:, :200] if k in ("pts_2d", "pts_3d") else v) for k, v in dl.items()}
+    for i in range(3):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            A, Bm = orc.reduce_translation(*orc._stack(dl["pts_2d"][i], dl["pts_3d"][i], None, None, dl["K"]))
+            exp = orc.solve_relaxation(A, Bm, max_iters=200000, variant="rc")
+        assert synth.rotation_angle(exp[0][0], rc.R[i, 0].cpu().numpy()) < ROT_TOL
+    with pytest.raises(NotImplementedError):
+        _solve(cb, dl, 300, 0, admm_dtype="f32")
+    assert small["pts_2d"].shape[1] == 200 and full.R.shape == rc.R.shape
+
+
+def test_null_scalar_and_plugin_vs_oracle(cb):
+    """The plugin class (K-first estimate_pose, benchmarks/toolkit/methods/p*.py) and the scalar functions against
+    the ORACLE (not against each other) on the harness's keyword layout (suite.py:80)."""
+    from cvxpnpl_b200 import synth
+    from oracle import cvxpnpl_oracle as orc
+    d = synth.make_batch(6, 7, 3, noise=1.0, seed=35)
+    for i in range(6):
+        kw = dict(pts_2d=d["pts_2d"][i], line_2d=d["line_2d"][i], pts_3d=d["pts_3d"][i], line_3d=d["line_3d"][i])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            exp = orc.pnpl(kw["pts_2d"], kw["line_2d"], kw["pts_3d"], kw["line_3d"], d["K"], max_iters=200000)
+            got = cb.CvxPnPL.estimate_pose(d["K"], **kw)
+            assert len(got) == len(exp) == 1
+            assert synth.rotation_angle(exp[0][0], got[0][0]) < ROT_TOL
+            assert np.linalg.norm(exp[0][1] - got[0][1]) / np.linalg.norm(exp[0][1]) < T_TOL
+            exp = orc.pnp(kw["pts_2d"], kw["pts_3d"], d["K"], max_iters=200000)
+            got = cb.CvxPnPL.estimate_pose(d["K"], pts_2d=kw["pts_2d"], pts_3d=kw["pts_3d"])
+            assert len(got) == len(exp) == 1 and synth.rotation_angle(exp[0][0], got[0][0]) < ROT_TOL
+    R, t = cb.null(d["pts_2d"][0], d["pts_3d"][0], d["K"])[0]
+    assert R.shape == (3, 3) and abs(np.linalg.det(R) - 1.0) < 1e-9
+
+
+def test_suite_cell_matches_oracle_on_same_problems(cb):
+    """one cell of the batched synthetic suite (cvxpnpl_b200/suite.py) -- the problems it
+    generates ON THE DEVICE are handed to the CPU oracle one by one, and the disambiguated pose / error metric
+    of the suite (suite.py:22-33, 95-108) is recomputed from the oracle's poses."""
+    from cvxpnpl_b200 import suite, synth
+    from oracle import cvxpnpl_oracle as orc
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    batch = suite.generate(96, 6, 0, 1.0, gen, torch.device("cuda"))
+    res = cb.solve_batched(batch["K"], pts_2d=batch["pts_2d"], pts_3d=batch["pts_3d"])
+    R, t = suite.disambiguate(res, batch, gen)
+    ang = suite.rotation_angle_deg(batch["R_gt"], R).cpu().numpy()
+    p2, p3, Kn = batch["pts_2d"].cpu().numpy(), batch["pts_3d"].cpu().numpy(), batch["K"].cpu().numpy()
+    Rg = batch["R_gt"].cpu().numpy()
+    for i in range(96):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            poses = orc.pnp(p2[i], p3[i], Kn, max_iters=200000)
+        assert len(poses) == int(res.n_poses[i])
+        if len(poses) == 1:
+            assert synth.rotation_angle(poses[0][0], R[i].cpu().numpy()) < ROT_TOL
+            assert abs(np.rad2deg(synth.rotation_angle(Rg[i], poses[0][0])) - ang[i]) < 1e-4
+
+
+def test_two_devices_one_process(cb):
+    """Kernel attributes (> 48 KB dynamic shared memory) are opted in per device: a second GPU driven from the
+    same process solves too.  Skipped on a single-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from cvxpnpl_b200 import synth
+    d = synth.make_batch(3000, 8, 4, noise=1.0, seed=17)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        K = torch.from_numpy(d["K"]).to(dev)
+        r = cb.solve_batched(K, pts_2d=torch.from_numpy(d["pts_2d"]).to(dev), pts_3d=torch.from_numpy(d["pts_3d"]).to(dev),
+                             line_2d=torch.from_numpy(d["line_2d"]).to(dev), line_3d=torch.from_numpy(d["line_3d"]).to(dev))
+        torch.cuda.synchronize(dev)
+        outs.append(r)
+    assert ((outs[0].status & 0xFF) == 0).all() and ((outs[1].status & 0xFF) == 0).all()
+    assert float((outs[0].R[:, 0].cpu() - outs[1].R[:, 0].cpu()).abs().max()) < 1e-8
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    import sys
+    sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+    import torch.distributed as dist
+    import cvxpnpl_b200 as cb
+    from cvxpnpl_b200 import synth
+    from cvxpnpl_b200.distributed import solve_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    total = 20_001
+    d = synth.make_batch(total, 8, 4, noise=1.0, seed=23)
+    dev = torch.device("cuda", rank)
+    full = {k: torch.from_numpy(d[k]).to(dev) for k in ("pts_2d", "pts_3d", "line_2d", "line_3d")}
+    K = torch.from_numpy(d["K"]).to(dev)
+    R, t, n, st, it = solve_sharded(K, **full)
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        one = cb.solve_batched(K, **full)
+        ok = (bool(((st & 0xFF) == 0).all()) and R.shape == (total, 3, 3)
+              and float((R - one.R[:, 0]).abs().max()) < 1e-8 and float((t - one.t[:, 0]).abs().max()) < 1e-8)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_solve_sharded_nccl(cb):
+    """cvxpnpl_b200.distributed.solve_sharded over NCCL: the batch sharded by contiguous ranges over every GPU of
+    the box (one process per GPU), rows all-gathered in place, result equal to the single-GPU solve.  On a
+    one-GPU box this still runs the NCCL path with world size 1."""
+    import socket
+    import torch.multiprocessing as mp
+    world = max(1, min(torch.cuda.device_count(), 8))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    assert sorted(res) == [(r, True) for r in range(world)]

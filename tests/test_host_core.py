@@ -145,9 +145,9 @@ def test_host_fp32_first_phase(n_pts, n_lines):
 def test_host_extraction_degenerate_big(name):
     """The device extraction routines (host build) on tests/golden/degenerate_big.npz: ST_SINGULAR exactly
     where the verbatim reference raised LinAlgError (cvxpnpl.py:165 / 212 / 510), the reference's number of
-    candidates, and every reproducible candidate (tests/degenerate_util.py) to 1e-6."""
+    candidates, and every reproducible candidate (oracle/candidate_sets.py) to 1e-6."""
     import os
-    from tests import degenerate_util as du
+    from oracle import candidate_sets as du
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "degenerate_big.npz"))
     total = stable = 0
     for i in range(len(g[name + "_err"])):

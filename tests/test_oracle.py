@@ -131,9 +131,9 @@ def test_degenerate_extraction_big(name):
     """tests/golden/degenerate_big.npz (generator make_degenerate_big.py, verbatim reference): 40 problems
     per family.  The oracle raises LinAlgError exactly where the reference did, returns the same number
     of candidates, and matches every candidate the reference itself reproduces under a 1e-14
-    perturbation of Z (tests/degenerate_util.py) to 1e-6."""
+    perturbation of Z (oracle/candidate_sets.py) to 1e-6."""
     import os
-    from tests import degenerate_util as du
+    from oracle import candidate_sets as du
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "degenerate_big.npz"))
     total = stable = 0
     for i in range(len(g[name + "_err"])):
