@@ -49,7 +49,7 @@ class Desc(ctypes.Structure):
         ("fp32_iters", ctypes.c_int32),
         ("timing", ctypes.c_int32),
         ("skip_prepass", ctypes.c_int32),
-        ("reserved3", ctypes.c_int32),
+        ("psd_mode", ctypes.c_int32),
         ("record", ctypes.c_void_p),
     ]
 

@@ -67,7 +67,7 @@ class Workspace:
 def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1e-9, max_iters=2500,
                   sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=True, variant="full", return_Z=False, return_obj=True, workspace=None,
                   out: Optional[BatchedPoses] = None, device=None, handoff=0, admm_dtype="f64",
-                  fp32_iters=400, timing=False, _prepass_hook=None, record=None) -> BatchedPoses:
+                  fp32_iters=400, timing=False, _prepass_hook=None, record=None, psd="track") -> BatchedPoses:
     """Solve B problems.  pts_2d [B,n,2], pts_3d [B,n,3], line_2d [B,m,2,2],
     line_3d [B,m,2,3], K [3,3] or [B,3,3]; any of the point / line pairs may be
     omitted (PnP / PnL / PnPL: cvxpnpl.py:523-627).  variant="rc" solves the ablation
@@ -77,6 +77,9 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
     admm_dtype="f32": "fp32 ADMM + fp64 extraction" (BASELINE.json configs[3]) -- the
     iterations that bring a problem into the linear tail run in FP32 (at most
     fp32_iters), the FP64 solver finishes to `eps`.
+    psd: PSD projection of the ADMM iteration -- "track" (default): two tracked eigenpairs refined once per
+    iteration with a certificate, problems that fail it are finished with the full decomposition; "full": a full
+    10x10 eigen-decomposition every iteration.
     record: optional [B,15] float64 CUDA tensor (may be a slice of an all-gather buffer) that the finish
     kernel fills with the packed row (R0 | t0 | n_poses | status | iters) of every problem."""
     _require_cuda()
@@ -122,6 +125,8 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         raise ValueError("variant must be 'full' or 'rc'")
     if admm_dtype not in ("f64", "f32"):
         raise ValueError("admm_dtype must be 'f64' or 'f32'")
+    if psd not in ("track", "full"):
+        raise ValueError("psd must be 'track' or 'full'")
     n_corr = (pts_2d.shape[1] if have_p else 0) + (line_2d.shape[1] if have_l else 0)
     if n_corr >= LARGE_N and B > 0:
         # many correspondences per problem (benchmarks/scalability/pnp.py:37-40): the
@@ -183,6 +188,7 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.handoff = int(handoff)
         d.fp32_iters = int(fp32_iters) if admm_dtype == "f32" else 0
         d.timing = int(bool(timing))
+        d.psd_mode = {"track": 0, "full": 1}[psd]
         d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
         if record is not None:
@@ -350,7 +356,7 @@ def measure_fp64_peak(device=None, iters=4000, repeats=5):
 
 
 KERNEL_NAMES = ("pre_kernel", "admm32_kernel", "ortho_kernel", "solve_fused_kernel", "straggler_kernel",
-                "solve_fused_kernel<resume>", "finish_kernel")
+                "solve_fused_kernel<resume>", "finish_kernel", "solve_track_kernel", "redecomp_kernel")
 
 
 def last_kernel_times():

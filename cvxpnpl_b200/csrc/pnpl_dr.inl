@@ -219,27 +219,12 @@ CVX_HD CVX_REAL jacobi_sweep(ArrT<S, CVX_REAL> T, ArrT<S, CVX_REAL> V)
 // rowk = 1 is the reference's SDP (22 equalities); rowk = 0 is the "rc" ablation of
 // benchmarks/toolkit/methods/rc.py:9-60 (the six row-orthonormality equalities removed).
 // ---------------------------------------------------------------------------------
+// Second half of a DR step: given Z = P_psd(M) in z[] (registers), X = P_aff(2 Z - M - Q/rho),
+// M += alpha (X - Z), G = alpha (X - Z); returns ||X - Z||_F^2.
 template <int S, class QR>
-CVX_HD CVX_REAL dr_step(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> V, ArrT<S, CVX_REAL> L, ArrT<S, CVX_REAL> G, QR qr, CVX_REAL alpha, CVX_REAL isig, CVX_REAL rowk,
-                      CVX_REAL z[55])
+CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr, CVX_REAL alpha, CVX_REAL isig, CVX_REAL rowk,
+                                 const CVX_REAL z[55])
 {
-#pragma unroll
-    for (int e = 0; e < 55; ++e) z[e] = CVX_REAL(0.0);
-#pragma unroll 1
-    for (int j = 0; j < 10; ++j) {
-        const CVX_REAL lj = L[j];
-        if (lj > CVX_REAL(0.0)) {
-            CVX_REAL v[10];
-#pragma unroll
-            for (int k = 0; k < 10; ++k) v[k] = V[k * 10 + j];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                const CVX_REAL lr = lj * v[r];
-#pragma unroll
-                for (int c = 0; c <= r; ++c) z[sidx(r, c)] = fma(lr, v[c], z[sidx(r, c)]);
-            }
-        }
-    }
     CVX_REAL res = CVX_REAL(0.0);
     const CVX_REAL inrm9 = CVX_REAL(1.0) / (CVX_REAL(2.0) + isig * isig);
 #define CVX_Q(i, j) (((i) < 9 && (j) < 9) ? qr[sidx(i, j)] : CVX_REAL(0.0))
@@ -302,5 +287,29 @@ CVX_HD CVX_REAL dr_step(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> V, ArrT<S, CVX_RE
     }
 #undef CVX_Q
     return res;
+}
+
+template <int S, class QR>
+CVX_HD CVX_REAL dr_step(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> V, ArrT<S, CVX_REAL> L, ArrT<S, CVX_REAL> G, QR qr, CVX_REAL alpha, CVX_REAL isig, CVX_REAL rowk,
+                      CVX_REAL z[55])
+{
+#pragma unroll
+    for (int e = 0; e < 55; ++e) z[e] = CVX_REAL(0.0);
+#pragma unroll 1
+    for (int j = 0; j < 10; ++j) {
+        const CVX_REAL lj = L[j];
+        if (lj > CVX_REAL(0.0)) {
+            CVX_REAL v[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) v[k] = V[k * 10 + j];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                const CVX_REAL lr = lj * v[r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) z[sidx(r, c)] = fma(lr, v[c], z[sidx(r, c)]);
+            }
+        }
+    }
+    return dr_affine_update(M, G, qr, alpha, isig, rowk, z);
 }
 

@@ -24,6 +24,7 @@
 #include "pnpl_extract.cuh"
 #include "pnpl_solve.cuh"
 #include "pnpl_warp.cuh"
+#include "pnpl_track.cuh"
 
 namespace {
 
@@ -37,8 +38,8 @@ thread_local int g_launches = 0;
 
 // optional per-kernel timing of the last `solve` (desc.timing != 0): CUDA events on the
 // caller's stream between the launches.  Slots: pre, admm32, ortho, fused, straggler,
-// resume, finish.
-constexpr int N_TIMED = 7;
+// resume, finish, track, redecomp.
+constexpr int N_TIMED = 9;
 thread_local cudaEvent_t g_ev[N_TIMED + 1];
 thread_local bool g_ev_ready = false;
 thread_local int g_ev_slot[N_TIMED + 1];   // kernel slot that starts at event i, -1 = end
@@ -202,7 +203,12 @@ __device__ __forceinline__ cvx::Problem problem_at(const cvxpnpl_b200_desc& d, i
 // of the batch (median ~300, tail to 2500) costs no idle lanes.
 // ---------------------------------------------------------------------------------
 // control words at the head of the workspace (unsigned long long each)
-enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3, CTRL_NEXT32 = 4, CTRL_ACTIVE = 5 };
+enum {
+    CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3, CTRL_NEXT32 = 4, CTRL_ACTIVE = 5,
+    CTRL_NFAIL = 6,      // problems the tracked solver handed back (failed certificate / stragglers): length of fail_list
+    CTRL_FAIL_NEXT = 7,  // queue head of the full-decomposition solver working on that list
+    CTRL_TRK_NEXT = 8    // queue head of the tracked solver
+};
 
 // RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
 //   is empty, a lane whose problem is still in its DR loop `grace` passes later hands it
@@ -215,7 +221,8 @@ enum { CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3
 template <bool RESUME>
 __global__ void __launch_bounds__(NT, 1)
 solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const double* pre, double* park,
-                   double* slab, const double* warm, const int32_t* order, int grace, int handoff_max, int64_t ws_stride)
+                   double* slab, const double* warm, const int32_t* order, int grace, int handoff_max, int64_t ws_stride,
+                   int from_track)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
@@ -243,7 +250,12 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
     bool exhausted = false;
     int drain = 0;   // passes since this lane saw the queue empty
     bool counted = false;   // this lane's problem is counted in ctrl[CTRL_ACTIVE]
-    const unsigned long long n_work = RESUME ? ctrl[CTRL_NSTRAG] : (unsigned long long)d.batch;
+    // from_track: the work is the list of problems the tracked solver handed back (order = that list, warm = their
+    // freshly decomposed state, see redecomp_kernel); its length is only known on the device
+    const unsigned long long n_work =
+        RESUME ? ctrl[CTRL_NSTRAG] : (from_track ? ctrl[CTRL_NFAIL] : (unsigned long long)d.batch);
+    const int q_next = RESUME ? CTRL_RESUME_NEXT : (from_track ? CTRL_FAIL_NEXT : CTRL_NEXT);
+    if (from_track && grace >= 0 && n_work <= (unsigned long long)handoff_max) grace = 1;   // fits the warp kernel
     cvx::LaneState st;
     st.finite = false;
     st.iterating = false;
@@ -257,17 +269,26 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
     int wslot = 0;   // warp-uniform history column
     for (;;) {
         if (b < 0 && !exhausted) {
-            const unsigned long long nb = atomicAdd(ctrl + (RESUME ? CTRL_RESUME_NEXT : CTRL_NEXT), 1ULL);
+            const unsigned long long nb = atomicAdd(ctrl + q_next, 1ULL);
             if (nb < n_work) {
                 if (RESUME) {
                     b = cvx::problem_resume(slab + nb * cvx::HAND_DOUBLES, V, M, L, QR, st);
                 } else {
                     b = (int64_t)order[nb];   // queue position -> problem (likely stragglers first)
-                    if (warm)   // the FP32 first phase has already brought the problem into the tail
+                    if (warm) {   // the FP32 first phase / the tracked solver has already advanced the problem
                         cvx::problem_begin_warm(pre + b * cvx::PRE_DOUBLES, warm + b * cvx::WARM_DOUBLES, o, V, M, L, QR,
                                                 st);
-                    else
+                        if (from_track) {
+                            const int fl = (int)pre[b * cvx::PRE_DOUBLES + cvx::TR_FLAGS];
+                            if (st.finite && (fl & 1)) {   // its DR loop was over already: only polish + park
+                                st.iterating = false;
+                                st.converged = (fl & 2) != 0;
+                                st.phase = 1;
+                            }
+                        }
+                    } else {
                         cvx::problem_begin(pre + b * cvx::PRE_DOUBLES, o, V, M, L, QR, st);
+                    }
                 }
             } else {
                 exhausted = true;
@@ -277,7 +298,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
         if (!RESUME && grace >= 0 && b >= 0 && st.iterating) {
             // hand-over: the queue is empty (nothing left to steal), this problem is still in
             // its DR loop `grace` passes later -> the warp-per-problem kernel finishes it
-            if (drain > 0 || *(volatile unsigned long long*)(ctrl + CTRL_NEXT) >= n_work) {
+            if (drain > 0 || *(volatile unsigned long long*)(ctrl + q_next) >= n_work) {
                 if (!counted) {
                     atomicAdd(ctrl + CTRL_ACTIVE, 1ULL);
                     counted = true;
@@ -312,6 +333,148 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
         }
     }
     tmem_free_all(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------
+// Tracked persistent solver (pnpl_track.cuh): same structure as solve_fused_kernel<false> -- one thread
+// per problem, 128 problems per CTA, one CTA per SM, lane-level work stealing from a difficulty-ordered
+// queue, Anderson history in tensor memory -- but the PSD projection comes from two tracked eigenpairs
+// refined once per iteration instead of a full 10x10 decomposition.  Per-problem shared memory:
+// M 55 | G 56 (the step; its first 36 words double as the Cholesky scratch of track_step between the
+// Anderson step and the next DR step) | U 20 | TH 2 | Q/rho 45 = 178 doubles.
+// A problem whose certificate fails (a third positive eigenvalue, or a slot that lost its vector), and a
+// straggler still iterating `grace` passes after the queue ran dry, goes back into its pre-pass record
+// and onto fail_list: redecomp_kernel + solve_fused_kernel<false>(from_track) finish those with the full
+// decomposition.
+// ---------------------------------------------------------------------------------
+constexpr int TRK_SMEM_DOUBLES = 55 + 56 + 20 + 2 + 45;
+constexpr size_t SMEM_TRK_BYTES = (size_t)NT * TRK_SMEM_DOUBLES * sizeof(double);
+__global__ void __launch_bounds__(NT, 1)
+solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double* pre, double* park, const double* warm,
+                   const int32_t* order, int32_t* fail_list, int grace, int handoff_max)
+{
+    extern __shared__ double smem[];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x;
+    cvx::Arr<NT> M{smem + tid};
+    cvx::Arr<NT> G{smem + (size_t)55 * NT + tid};
+    cvx::Arr<NT> U{smem + (size_t)111 * NT + tid};
+    cvx::Arr<NT> TH{smem + (size_t)131 * NT + tid};
+    cvx::Arr<NT> QR{smem + (size_t)133 * NT + tid};
+    const uint32_t tmem_base = tmem_alloc_all(&tmem_slot);
+    const HistTmem H{tmem_base + ((uint32_t)((tid >> 5) & 3) << 21)};
+    {
+        uint32_t zero[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) zero[u] = 0u;
+        for (int c = 0; c < cvx::AA_WORDS / 32; ++c) H.st<32>(32 * c, zero);
+        H.wait_st();
+    }
+    G[55] = 0.0;   // zero pad read by the 8-word chunks of aa_step (neither the step nor the Cholesky scratch reach it)
+    const cvx::AnyLane any;
+    int64_t b = -1;
+    bool exhausted = false;
+    int drain = 0;
+    bool counted = false;
+    const unsigned long long n_work = (unsigned long long)d.batch;
+    cvx::LaneState st;
+    st.finite = false;
+    st.iterating = false;
+    st.converged = false;
+    st.it = 0;
+    st.phase = 0;
+    st.rho = 0.0;
+    st.dobj = 0.0;
+    st.res_prev = 1e300;
+    cvx::aa_reset(st.aa);
+    int wslot = 0;
+    for (;;) {
+        if (b < 0 && !exhausted) {
+            const unsigned long long nb = atomicAdd(ctrl + CTRL_TRK_NEXT, 1ULL);
+            if (nb < n_work) {
+                b = (int64_t)order[nb];
+                if (warm)
+                    cvx::track_begin_warm(pre + b * cvx::PRE_DOUBLES, warm + b * cvx::WARM_DOUBLES, o, M, U, TH, QR, st);
+                else
+                    cvx::track_begin(pre + b * cvx::PRE_DOUBLES, o, M, U, TH, QR, st);
+            } else {
+                exhausted = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, b < 0)) break;
+        bool give_up = false;
+        if (grace >= 0 && b >= 0 && st.iterating) {
+            if (drain > 0 || *(volatile unsigned long long*)(ctrl + CTRL_TRK_NEXT) >= n_work) {
+                if (!counted) {
+                    atomicAdd(ctrl + CTRL_ACTIVE, 1ULL);
+                    counted = true;
+                }
+                ++drain;
+            }
+            give_up = drain > grace && *(volatile unsigned long long*)(ctrl + CTRL_ACTIVE) <= (unsigned long long)handoff_max;
+        }
+        bool want = false;
+        if (b >= 0 && !give_up) want = cvx::track_pass_dr(o, M, G, U, TH, QR, st);
+        __syncwarp();
+        if (H.any(want)) cvx::aa_step(M, G, H, st.aa, want, wslot, (float)st.res_prev);
+        wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
+        if (b >= 0) {
+            const int rc = give_up ? -1 : cvx::track_pass_eig(o, M, U, TH, G, QR, st, any);
+            if (rc > 0) {
+                cvx::track_park(o, U, TH, st, park + b * cvx::PARK_DOUBLES, d.iters + b);
+                b = -1;
+            } else if (rc < 0) {
+                cvx::track_handoff(M, QR, st, pre + b * cvx::PRE_DOUBLES);
+                fail_list[atomicAdd(ctrl + CTRL_NFAIL, 1ULL)] = (int32_t)b;
+                b = -1;
+                if (give_up) exhausted = true;
+            }
+            if (counted && (b < 0 || !st.iterating)) {
+                atomicAdd(ctrl + CTRL_ACTIVE, ~0ULL);
+                counted = false;
+            }
+        }
+    }
+    tmem_free_all(tmem_base);
+}
+
+// Problems handed back by the tracked solver: cold eigen-decomposition of their DR iterate M (cyclic Jacobi,
+// lane-parallel), exported in the WARM format the full-decomposition solver starts from.
+constexpr int NT_R = 64;
+constexpr size_t SMEM_R_BYTES = (size_t)NT_R * 100 * sizeof(double);
+__global__ void __launch_bounds__(NT_R) redecomp_kernel(const unsigned long long* ctrl, const int32_t* fail_list,
+                                                        const double* pre, double* warm)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const unsigned long long k = (unsigned long long)blockIdx.x * NT_R + tid;
+    if (k >= ctrl[CTRL_NFAIL]) return;
+    const int64_t b = fail_list[k];
+    const double* rec = pre + b * cvx::PRE_DOUBLES;
+    double* w = warm + b * cvx::WARM_DOUBLES;
+    cvx::Arr<NT_R> V{smem + tid};
+    double t[55];
+#pragma unroll
+    for (int e = 0; e < 55; ++e) {
+        t[e] = rec[cvx::TR_M + e];
+        w[e] = t[e];
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int s = 0; s < 12; ++s) {
+        double dg = 0;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) dg = fma(t[cvx::sidx(j, j)], t[cvx::sidx(j, j)], dg);
+        if (!(cvx::jacobi_sweep_reg(t, V) > 1e-26 * dg)) break;
+    }
+#pragma unroll 4
+    for (int e = 0; e < 100; ++e) w[55 + e] = V[e];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) w[155 + j] = t[cvx::sidx(j, j)];
+    w[165] = rec[cvx::TR_IT];
 }
 
 // ---------------------------------------------------------------------------------
@@ -440,6 +603,7 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
 // ---------------------------------------------------------------------------------
 constexpr int NT_P = 64;
 constexpr size_t SMEM_P_BYTES = (size_t)NT_P * 100 * sizeof(double);   // V (T stays in registers)
+constexpr size_t SMEM_PE_BYTES = (size_t)NT_P * SMEM_DOUBLES * sizeof(double);   // with the early iterations: V, M, T, lambda
 // Difficulty-ordered work queue.  The slow problems of a batch are the ones whose optimal face
 // is nearly flat: two small eigenvalues of Q (measured on seeded batches: 90 % of the 1 % slowest
 // problems are among the quarter of the batch with the smallest second eigenvalue).  The
@@ -467,6 +631,9 @@ __device__ __forceinline__ int difficulty_bucket(const double* rec, const Opts& 
     return k < 0 ? 0 : (k > N_BUCKETS - 1 ? N_BUCKETS - 1 : k);
 }
 
+// EARLY: also run the first TRK_EARLY DR iterations with the full decomposition (all lanes in the same phase) and
+// leave the record in the tracked solver's format (pnpl_track.cuh).
+template <bool EARLY>
 __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre, unsigned* bucket_count,
                                                    unsigned char* bucket_of, int64_t first, int64_t last)
 {
@@ -481,6 +648,12 @@ __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, 
     const int k = (o.kappa != 0.0) ? difficulty_bucket(out, o) : 0;
     bucket_of[b] = (unsigned char)k;
     atomicAdd(bucket_count + k, 1u);
+    if (EARLY) {
+        cvx::Arr<NT_P> M{smem + (size_t)100 * NT_P + tid};
+        cvx::Arr<NT_P> T{smem + (size_t)155 * NT_P + tid};
+        cvx::Arr<NT_P> L{smem + (size_t)211 * NT_P + tid};
+        cvx::track_early(out, o, V, M, T, L);
+    }
 }
 
 // counting sort of the buckets -> queue order (likely stragglers first)
@@ -932,7 +1105,7 @@ int64_t device_slots(int64_t batch)
 //                    pre-pass 46 x batch doubles | hand-over slab 216 x slots doubles |
 //                    AA history AA_WORDS x slots words (stage kernel only; the fused kernel uses TMEM) |
 //                    FP32-phase export 166 x batch doubles | FP32 Q/rho 45 x 2 slots floats |
-//                    queue order batch x int32 | difficulty bucket batch x byte]
+//                    queue order batch x int32 | hand-back list batch x int32 | difficulty bucket batch x byte]
 size_t ws_bytes_for(int64_t slots, int64_t batch)
 {
     return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES) +
@@ -941,8 +1114,8 @@ size_t ws_bytes_for(int64_t slots, int64_t batch)
            (size_t)slots * cvx::AA_WORDS * sizeof(float) +
            // FP32 first phase: exported state per problem, Q/rho scratch of its 2x wider grid
            (size_t)batch * cvx::WARM_DOUBLES * sizeof(double) + (size_t)slots * 2 * 45 * sizeof(float) +
-           // queue order (int32) and bucket (byte) per problem
-           (((size_t)batch * 5 + 15) / 16) * 16;
+           // queue order (int32), list of problems handed back by the tracked solver (int32) and bucket (byte) per problem
+           (((size_t)batch * 9 + 15) / 16) * 16;
 }
 
 }  // namespace
@@ -984,7 +1157,14 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(straggler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W_BYTES);
             if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_P_BYTES);
+                e = cudaFuncSetAttribute(pre_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_P_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(pre_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PE_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(solve_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_TRK_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(redecomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_R_BYTES);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(admm32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM32_BYTES);
             if (e == cudaSuccess)
@@ -1017,21 +1197,31 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         cudaError_t e0 = cudaMemsetAsync(ctrl, 0, WS_HEADER_DOUBLES * sizeof(double), st);
         if (e0 != cudaSuccess) return fail((int)e0, cudaGetErrorString(e0));
     }
+    // PSD projection: tracked eigenpairs (default) or the full decomposition every iteration (desc.psd_mode = 1;
+    // also for batches that fit the warp-per-problem grid, which go there at once)
+    const bool tracked = d->psd_mode == 0 && d->batch > n_sm * 2 * (NT_W / 32);
+    const bool early = tracked && d->fp32_iters <= 0;   // the FP32 first phase starts from the start decomposition
     const bool tm = d->timing != 0 && mode != 1;
     g_ev_n = 0;
     // regions behind the hand-over slab (see ws_bytes_for)
     double* warm = (double*)((uint32_t*)(slab + slots * cvx::HAND_DOUBLES) + slots * cvx::AA_WORDS);
     float* qr32 = (float*)(warm + d->batch * cvx::WARM_DOUBLES);
     int32_t* order = (int32_t*)(qr32 + slots * 2 * 45);
-    unsigned char* bucket_of = (unsigned char*)(order + d->batch);
+    int32_t* fail_list = order + d->batch;
+    unsigned char* bucket_of = (unsigned char*)(fail_list + d->batch);
     unsigned* bucket_count = (unsigned*)(ctrl + 16);
     unsigned* bucket_offset = bucket_count + N_BUCKETS;
     mark(tm, 0, st);
     if (mode != 2) {
         const int64_t lo = mode == 1 ? first : 0, hi = mode == 1 ? first + count : d->batch;
-        if (hi > lo)
-            pre_kernel<<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(dd, o, pre, bucket_count,
-                                                                                         bucket_of, lo, hi);
+        if (hi > lo) {
+            if (early)
+                pre_kernel<true><<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_PE_BYTES, st>>>(
+                    dd, o, pre, bucket_count, bucket_of, lo, hi);
+            else
+                pre_kernel<false><<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(
+                    dd, o, pre, bucket_count, bucket_of, lo, hi);
+        }
         if (mode == 1) {
             g_launches = 1;
             cudaError_t e1 = cudaGetLastError();
@@ -1064,15 +1254,27 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     if (wblocks > wcap) wblocks = wcap;
     // (two or three problems per warp were measured too: no difference)
     const int handoff_max = (int)(wblocks * warps_per_cta);
-    mark(tm, 3, st);
-    solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm_in, order,
-                                                                        grace, handoff_max, slots);
+    if (tracked) {
+        mark(tm, 7, st);
+        solve_track_kernel<<<(unsigned)blocks, NT, SMEM_TRK_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order, fail_list,
+                                                                         grace, handoff_max);
+        mark(tm, 8, st);
+        redecomp_kernel<<<(unsigned)((d->batch + NT_R - 1) / NT_R), NT_R, SMEM_R_BYTES, st>>>(ctrl, fail_list, pre, warm);
+        mark(tm, 3, st);
+        solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm, fail_list,
+                                                                            grace, handoff_max, slots, 1);
+        g_launches += 2;
+    } else {
+        mark(tm, 3, st);
+        solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm_in, order,
+                                                                            grace, handoff_max, slots, 0);
+    }
     if (grace >= 0) {
         mark(tm, 4, st);
         straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab);
         mark(tm, 5, st);
         solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, nullptr,
-                                                                          -1, 0, slots);
+                                                                          -1, 0, slots, 0);
         g_launches += 2;
     }
     mark(tm, 6, st);
@@ -1095,7 +1297,7 @@ int cvxpnpl_b200_prepass(const cvxpnpl_b200_desc* d, int64_t first, int64_t coun
 
 int cvxpnpl_b200_kernel_times(float* ms, int n)
 {
-    if (!ms || n < N_TIMED) return fail(-5, "kernel_times needs room for 7 floats");
+    if (!ms || n < N_TIMED) return fail(-5, "kernel_times needs room for 9 floats");
     for (int i = 0; i < n; ++i) ms[i] = 0.f;
     if (g_ev_n < 2) return fail(-9, "the last solve on this thread was not timed (desc.timing = 0)");
     cudaError_t e = cudaEventSynchronize(g_ev[g_ev_n - 1]);

@@ -87,7 +87,10 @@ typedef struct cvxpnpl_b200_desc {
                                tail run in FP32 (at most this many), the FP64 solver finishes to `eps` */
     int32_t timing;         /* != 0: record CUDA events between the kernels of `solve` (cvxpnpl_b200_kernel_times) */
     int32_t skip_prepass;   /* != 0: the pre-pass of every problem has been run by cvxpnpl_b200_prepass already */
-    int32_t reserved3;
+    int32_t psd_mode;       /* PSD projection of the ADMM iteration.  0 = default: two tracked eigenpairs refined once per
+                               iteration, with a Cholesky certificate that nothing else in the spectrum is positive (problems
+                               that fail it are finished with the full decomposition); 1 = full 10x10 eigen-decomposition
+                               (warm-started Jacobi sweep) every iteration */
     /* ---- packed output (optional) ---- */
     double* record;         /* optional [B, 15]: R of candidate 0 (9, row-major) | t (3) | n_poses | status | iters,
                                written by the finish kernel next to R / t: the row a multi-GPU caller all-gathers
@@ -117,8 +120,8 @@ int cvxpnpl_b200_solve(const cvxpnpl_b200_desc* desc, void* stream);
 int cvxpnpl_b200_prepass(const cvxpnpl_b200_desc* desc, int64_t first, int64_t count, void* stream);
 
 /* Device time of each kernel of the last `solve` issued by this host thread with
- * desc.timing != 0, in ms: pre, admm32, ortho, solve_fused, straggler, resume, finish
- * (0 for kernels that were not launched).  Synchronises on the last event. */
+ * desc.timing != 0, in ms: pre, admm32, ortho, solve_fused, straggler, resume, finish, solve_track,
+ * redecomp (n >= 9; 0 for kernels that were not launched).  Synchronises on the last event. */
 int cvxpnpl_b200_kernel_times(float* ms, int n);
 
 /* Stage: correspondences -> Q [B,9,9] (= A'A of cvxpnpl.py:475) and Bmat [B,3,9]

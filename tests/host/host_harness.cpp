@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../cvxpnpl_b200/csrc/pnpl_solve.cuh"
+#include "../../cvxpnpl_b200/csrc/pnpl_track.cuh"
 
 extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
                           const double* pts_2d, const double* pts_3d, const double* line_2d,
@@ -114,3 +115,106 @@ extern "C" int host_quartic(const double* c, double* x) { return cvx::quartic_re
 
 // plateau detector of pass_dr / the warp kernel (pnpl_solve.cuh): returns the jump length (0: none)
 extern "C" int host_plateau_update(int32_t* plat, double res2, double res2_prev) { return cvx::plateau_update(*plat, res2, res2_prev); }
+
+
+// The tracked solver (pnpl_track.cuh) exactly as the CUDA kernels chain it: pre-pass (assembly, start
+// decomposition, TRK_EARLY full iterations) -> tracked DR loop with Anderson steps -> park -> extraction.
+// A problem whose certificate fails continues like the warp-per-problem kernel does: cold full
+// decomposition of its M, full-decomposition DR loop.  fallbacks[b] = 1 for those.
+extern "C" int host_solve_track(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
+                                const double* pts_2d, const double* pts_3d, const double* line_2d,
+                                const double* line_3d, double eps, int max_iters, double rho_rel, double alpha,
+                                double sigma, int anderson, int variant, double* R, double* t, int32_t* n_poses,
+                                int32_t* status, int32_t* iters, double* obj, double* Z, int32_t* fallbacks)
+{
+    cvx::Opts o;
+    o.eps2 = eps * eps;
+    o.alpha = alpha;
+    o.rho_rel = rho_rel;
+    o.max_iters = max_iters > 0 ? max_iters : 2500;
+    o.sweeps = 1;
+    o.sigma = sigma;
+    cvx::default_params(n_pts, o.rho_rel, o.alpha, o.sigma);
+    o.anderson = anderson != 0;
+    o.rowk = variant == 1 ? 0.0 : 1.0;
+    o.kappa = cvx::DUAL_GUESS;
+    o.aa_on2 = cvx::AA_RES2_ON;
+    std::vector<double> V(100), M(56), T(56), L(10), qr(45), U(20), TH(2), BS(36), Qs(45), Bs(27);
+    std::vector<uint32_t> hist(cvx::AA_WORDS, 0u);
+    const cvx::AnyLane any;
+    for (int64_t b = 0; b < B; ++b) {
+        cvx::Problem pr;
+        pr.K = k_batched ? K + 9 * b : K;
+        pr.pts_2d = pts_2d + b * 2 * n_pts;
+        pr.pts_3d = pts_3d + b * 3 * n_pts;
+        pr.line_2d = line_2d + b * 4 * n_lines;
+        pr.line_3d = line_3d + b * 6 * n_lines;
+        pr.n_pts = n_pts;
+        pr.n_lines = n_lines;
+        cvx::Arr<1> aV{V.data()}, aM{M.data()}, aT{T.data()}, aL{L.data()}, aQ{qr.data()}, aU{U.data()}, aTH{TH.data()},
+            aBS{BS.data()};
+        double rec[cvx::PRE_DOUBLES], park[cvx::PARK_DOUBLES];
+        cvx::assemble_scaled(pr, o, rec);
+        cvx::start_decomposition(rec, o, aV);
+        cvx::track_early(rec, o, aV, aM, aT, aL);
+        cvx::LaneState st;
+        cvx::track_begin(rec, o, aM, aU, aTH, aQ, st);
+        const cvx::HistMem H{hist.data(), 1};
+        T[55] = 0.0;
+        int wslot = 0;
+        int32_t it_out = 0;
+        bool handed = false;
+        for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+            const bool want = cvx::track_pass_dr(o, aM, aT, aU, aTH, aQ, st);
+            if (want) cvx::aa_step(aM, aT, H, st.aa, want, wslot, (float)st.res_prev);
+            wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
+            const int rc = cvx::track_pass_eig(o, aM, aU, aTH, aBS, aQ, st, any);
+            if (rc > 0) break;
+            if (rc < 0) {
+                handed = true;
+                break;
+            }
+        }
+        cvx::Result rs;
+        if (handed) {
+            // what straggler_kernel does: cold decomposition of M, then the full-decomposition loop
+            cvx::track_handoff(aM, aQ, st, rec);
+            for (int e = 0; e < 55; ++e) T[e] = M[e];
+            for (int i = 0; i < 10; ++i)
+                for (int j = 0; j < 10; ++j) V[i * 10 + j] = (i == j);
+            for (int s = 0; s < 12; ++s) {
+                double dg = 0;
+                for (int j = 0; j < 10; ++j) dg += T[cvx::sidx(j, j)] * T[cvx::sidx(j, j)];
+                if (!(cvx::jacobi_sweep(aT, aV) > 1e-26 * dg)) break;
+            }
+            for (int j = 0; j < 10; ++j) L[j] = T[cvx::sidx(j, j)];
+            T[55] = 0.0;
+            cvx::aa_reset(st.aa);
+            st.res_prev = 1e300;
+            st.phase = st.iterating ? 0 : 1;
+            for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+                const bool want = cvx::pass_dr(o, aV, aM, aT, aL, aQ, st);
+                if (want) cvx::aa_step(aM, aT, H, st.aa, want, wslot, (float)st.res_prev);
+                wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
+                if (cvx::pass_eig(o, aV, aM, aT, aL, aQ, st)) break;
+            }
+            cvx::problem_park(aV, aL, st, park, &it_out);
+        } else {
+            cvx::track_park(o, aU, aTH, st, park, &it_out);
+        }
+        cvx::extract_parked(pr, o, park, aV, cvx::Arr<1>{Qs.data()}, cvx::Arr<1>{Bs.data()}, R + b * 36, t + b * 12,
+                            Z ? Z + b * 100 : nullptr, rs);
+        n_poses[b] = rs.n_poses;
+        status[b] = rs.status;
+        iters[b] = it_out;
+        if (fallbacks) fallbacks[b] = handed ? 1 : 0;
+#if defined(CVX_TRK_DEBUG)
+        if (b == B - 1) printf("track_step calls %ld over %ld passes\n", cvx::g_track_steps, cvx::g_track_passes);
+#endif
+        if (obj) {
+            obj[2 * b] = rs.pobj;
+            obj[2 * b + 1] = rs.dobj;
+        }
+    }
+    return 0;
+}
