@@ -212,13 +212,27 @@ CVX_HD int track_step(Arr<S> M, Arr<S> U, Arr<S> TH, Arr<S> Bs, double& corr2, c
     const bool pos0 = th0 > 0.0, pos1 = th1 > 0.0;
     const double s0 = pos0 ? th0 : 0.0, s1 = pos1 ? th1 : 0.0;
     double x0[8], x1[8];
-    const bool ok0 = chol8_solve(Bs, s0, ct0, x0, true);
-    const bool ok1 = chol8_solve(Bs, s1, ct1, x1, true);
-    bool ok2 = true;
-    if (any(pos0 && pos1)) {
-        double dummy[8];
-        ok2 = chol8_solve(Bs, 0.0, ct0, dummy, false);
-        if (!(pos0 && pos1)) ok2 = true;
+    bool ok0 = true, ok1 = true, ok2 = true;
+    // slot 0, slot 1, and (only when both slots are positive) the certificate at shift 0: one rolled loop, so
+    // the factorisation exists once in the instruction stream (the loop body then runs from the instruction cache)
+    const int n_fact = (pos0 && pos1) ? 3 : 2;
+#pragma unroll 1
+    for (int q = 0; q < n_fact; ++q) {
+        double rhs[8], x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rhs[i] = (q == 0) ? ct0[i] : ct1[i];
+        const bool okq = chol8_solve(Bs, q == 0 ? s0 : (q == 1 ? s1 : 0.0), rhs, x, true);
+        if (q == 0) {
+            ok0 = okq;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x0[i] = x[i];
+        } else if (q == 1) {
+            ok1 = okq;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x1[i] = x[i];
+        } else {
+            ok2 = okq;
+        }
     }
     int rc = (ok0 && ok1 && ok2) ? TRK_OK : TRK_NEED_FULL;
 #if defined(CVX_TRK_DEBUG) && !defined(__CUDA_ARCH__)
@@ -514,19 +528,17 @@ CVX_HD int track_pass_eig(const Opts& o, Arr<S> M, Arr<S> U, Arr<S> TH, Arr<S> B
     ++g_track_passes;
 #endif
     double corr2 = 0.0;
-    int rc = track_step(M, U, TH, BS, corr2, any);
+    int rc = TRK_OK;
     // One step per DR iteration is enough even right after a plateau jump or an extrapolation (measured,
     // host build: repeating the step whenever the correction is large changes neither the iteration
-    // counts nor the poses).  Only a FAILED certificate is looked at again when the step it was computed
-    // in was far from converged: B is the complement of the vectors BEFORE the step, and with a large
-    // correction it still contains what the slots have not picked up yet.
+    // counts nor the poses).  Only a FAILED certificate is looked at again (up to three times) when the
+    // step it was computed in was far from converged: B is the complement of the vectors BEFORE the step,
+    // and with a large correction it still contains what the slots have not picked up yet.
+    // (One rolled loop so that the step exists once in the instruction stream.)
 #pragma unroll 1
-    for (int k = 0; k < 3 && any(rc != TRK_OK && corr2 > CVX_TRK_REPEAT2); ++k) {
-        if (rc != TRK_OK && corr2 > CVX_TRK_REPEAT2) {
-            double c2 = 0.0;
-            rc = track_step(M, U, TH, BS, c2, any);
-            corr2 = c2;
-        }
+    for (int k = 0; k < 4; ++k) {
+        rc = track_step(M, U, TH, BS, corr2, any);
+        if (!(rc != TRK_OK && corr2 > CVX_TRK_REPEAT2)) break;
     }
     if (rc != TRK_OK) return -1;
     if (st.iterating) {
