@@ -412,6 +412,52 @@ CVX_HD void unpack_h2(uint32_t w, float& lo, float& hi)
 #endif
 }
 
+// Mixed-precision FMA  acc + half(a) * half(b)  in FP32: one instruction on sm_100a (SASS FHFMA, the operand
+// halves are selected inside the instruction), so a dot product with an FP16-pair history column needs no
+// unpacking.  The product of two FP16 numbers is exact in FP32, so host and device agree bit for bit.
+CVX_HD float hfma_ll(uint32_t a, uint32_t b, float acc)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("{.reg .f16 al, ah, bl, bh; mov.b32 {al, ah}, %1; mov.b32 {bl, bh}, %2; fma.rn.f32.f16 %0, al, bl, %3;}"
+        : "=f"(r) : "r"(a), "r"(b), "f"(acc));
+    return r;
+#else
+    float al, ah, bl, bh;
+    unpack_h2(a, al, ah);
+    unpack_h2(b, bl, bh);
+    return fmaf(al, bl, acc);
+#endif
+}
+CVX_HD float hfma_hh(uint32_t a, uint32_t b, float acc)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("{.reg .f16 al, ah, bl, bh; mov.b32 {al, ah}, %1; mov.b32 {bl, bh}, %2; fma.rn.f32.f16 %0, ah, bh, %3;}"
+        : "=f"(r) : "r"(a), "r"(b), "f"(acc));
+    return r;
+#else
+    float al, ah, bl, bh;
+    unpack_h2(a, al, ah);
+    unpack_h2(b, bl, bh);
+    return fmaf(ah, bh, acc);
+#endif
+}
+CVX_HD float hfma_hl(uint32_t a, uint32_t b, float acc)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("{.reg .f16 al, ah, bl, bh; mov.b32 {al, ah}, %1; mov.b32 {bl, bh}, %2; fma.rn.f32.f16 %0, ah, bl, %3;}"
+        : "=f"(r) : "r"(a), "r"(b), "f"(acc));
+    return r;
+#else
+    float al, ah, bl, bh;
+    unpack_h2(a, al, ah);
+    unpack_h2(b, bl, bh);
+    return fmaf(ah, bl, acc);
+#endif
+}
+
 // power of two s with |g| s in [16, 64) for |g|^2 ~ res2 (the squared DR residual)
 CVX_HD float aa_scale(float res2)
 {
@@ -459,7 +505,7 @@ CVX_HD void aa_ld_cols(const Hist& H, int off, int c, uint32_t w[28])
     H.template ld<4>(off + c * 28 + 24, w + 24);
 }
 
-// One accelerated step.  `active` lanes own a problem in the tail of its DR
+// (round-1 form, kept for A/B runs: -DCVX_AA_V1)  One accelerated step.  `active` lanes own a problem in the tail of its DR
 // iteration; `wslot` (warp-uniform, cycles 0..AA_M-1) is the column overwritten now;
 // res2 is the squared DR residual of the iterate (sets the FP16 scale).  On entry M
 // holds M_k + g_k and G holds g_k (G[55] is a dedicated zero so whole 8-entry chunks
@@ -467,7 +513,7 @@ CVX_HD void aa_ld_cols(const Hist& H, int off, int c, uint32_t w[28])
 // The least squares runs on FP32 sums with an FP32 Cholesky factorisation.  The
 // Gram matrix is kept across steps; only the row of the new column is recomputed.
 template <int S, class RT, class Hist>
-CVX_HD void aa_step(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bool active, int wslot, float res2)
+CVX_HD void aa_step_v1(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bool active, int wslot, float res2)
 {
     const bool close = active && aa.have_prev;
     // the scale may grow at most 4x per step: then (|g_{k-1}| + |g_k|) s_k and the stored
@@ -683,6 +729,261 @@ CVX_HD void aa_step(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bo
     aa.have_prev = active;
     aa.scale_prev = sc;
 }
+
+// One accelerated step.  `active` lanes own a problem in the tail of its DR
+// iteration; `wslot` (warp-uniform, cycles 0..AA_M-1) is the column overwritten now;
+// res2 is the squared DR residual of the iterate (sets the FP16 scale).  On entry M
+// holds M_k + g_k and G holds g_k (G[55] is a dedicated zero so whole 8-entry chunks
+// can be processed without a bounds test); on exit (active lanes) M holds M_{k+1}.
+// The least squares runs on FP32 sums with an FP32 Cholesky factorisation.  The
+// Gram matrix is kept across steps; only the row of the new column is recomputed.
+//
+// Instruction budget (with the tracked PSD projection this step was half of the solver's
+// instructions; ncu, profiles/r2c):
+//   * every product with a history column is ONE mixed-precision FMA on the packed FP16 pair
+//     (hfma_*: SASS FHFMA) -- no unpacking;
+//   * the right-hand side  rg_j = col_j . g_k  is not recomputed: g_k = g_{k-1} + dg, and
+//     col_j . dg is the Gram row nd_j that is computed anyway, so rg_j += nd_j / s (the FP16-rounded
+//     dg is used, i.e. the least squares sees g up to the rounding of its last <= AA_M differences: a
+//     column lives AA_M steps, then its rg is set afresh);  rg lives next to the Gram matrix;
+//   * the coefficients gamma_j enter the extrapolation as FP16 numbers (common power-of-two scale), again
+//     one FHFMA per entry.  The extrapolation only steers the iteration; the fixed point does not depend
+//     on it.  Measured (host build, 3000 problems each): same iteration counts as the round-1 form.
+constexpr int AA_OFF_RG = AA_OFF_GRAM + AA_GRAM_WORDS;   // 504: rg_0..6 (words 504..507 travel with the Gram block)
+static_assert(AA_OFF_RG + 8 <= AA_WORDS, "rg does not fit");
+template <int S, class RT, class Hist>
+CVX_HD void aa_step(ArrT<S, RT> M, ArrT<S, RT> G, const Hist& H, AAState& aa, bool active, int wslot, float res2)
+{
+    const bool close = active && aa.have_prev;
+    // the scale may grow at most 4x per step: then (|g_{k-1}| + |g_k|) s_k and the stored
+    // step (at most 10 |g|) stay far below the FP16 maximum however fast the residual drops
+    const float sc = close ? fminf(aa_scale(res2), 4.f * aa.scale_prev) : aa_scale(res2);
+    const float ratio = sc / aa.scale_prev;   // both powers of two
+    // ---- A. close the newest column (dG = g_k - g_{k-1}, dM + dG = step_{k-1} + dG);
+    //         Gram row of the new column ---------------------------------------------------
+    float nd[AA_M];              // dg_new . col_j  (col_wslot is the one being replaced)
+    float ndd = 0.f, ndg = 0.f;  // dg_new . dg_new, dg_new . g
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) nd[j] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < AA_CHUNKS; ++c) {
+        uint32_t gpw[8], spw[4], cw[28], dgw[4], dsw[4];
+        H.template ld<8>(AA_OFF_GP + 8 * c, gpw);
+        H.template ld<4>(AA_OFF_SP + 4 * c, spw);
+        aa_ld_cols(H, AA_OFF_DG, c, cw);
+        H.wait_ld();
+        float gf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gf[u] = (float)G[c * 8 + u];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            float s0, s1, r0, r1;
+            unpack_h2(spw[w], s0, s1);
+            const float d0 = (gf[2 * w] - w2f(gpw[2 * w])) * sc, d1 = (gf[2 * w + 1] - w2f(gpw[2 * w + 1])) * sc;
+            // a column that is not closed is stored as zeros (never garbage: 0 * Inf = NaN)
+            dgw[w] = close ? pack_h2(d0, d1) : 0u;
+            dsw[w] = close ? pack_h2(fmaf(s0, ratio, d0), fmaf(s1, ratio, d1)) : 0u;
+            unpack_h2(dgw[w], r0, r1);   // the rounded column is the one that counts
+            ndd = fmaf(r0, r0, fmaf(r1, r1, ndd));
+            ndg = fmaf(r0, gf[2 * w], fmaf(r1, gf[2 * w + 1], ndg));
+        }
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) nd[j] = hfma_hh(cw[4 * j + w], dgw[w], hfma_ll(cw[4 * j + w], dgw[w], nd[j]));
+        H.template st<4>(AA_OFF_DG + c * 28 + 4 * wslot, dgw);
+        H.template st<4>(AA_OFF_DS + c * 28 + 4 * wslot, dsw);
+    }
+    // the overwritten slot is valid only if this lane had a previous iterate
+    aa.mask = close ? (aa.mask | (1u << wslot)) : (aa.mask & ~(1u << wslot));
+    if (!active) aa.mask = 0u;
+    // refresh row / column wslot of the Gram matrix; right-hand side rg_j += nd_j / s (new column: dg . g)
+    float gram[32], rg[AA_M];
+    {
+        uint32_t gw[32], rw[4];
+        H.template ld<32>(AA_OFF_GRAM, gw);
+        H.template ld<4>(AA_OFF_RG + 4, rw);
+        H.wait_ld();
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const int e = (i * (i + 1)) / 2 + j;
+                float v = w2f(gw[e]);
+                if (i == wslot && j == wslot) v = ndd;
+                else if (i == wslot) v = nd[j];
+                else if (j == wslot) v = nd[i];
+                gram[e] = v;
+                gw[e] = f2w(v);
+            }
+        const float isc = 1.f / sc;
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j) {
+            const float prev = w2f(j < 4 ? gw[AA_GRAM_WORDS + j] : rw[j - 4]);
+            rg[j] = (j == wslot) ? ndg : fmaf(nd[j], isc, prev);
+            if (j < 4) gw[AA_GRAM_WORDS + j] = f2w(rg[j]);
+            else rw[j - 4] = f2w(rg[j]);
+        }
+        rw[3] = 0u;
+        H.template st<32>(AA_OFF_GRAM, gw);
+        H.template st<4>(AA_OFF_RG + 4, rw);
+    }
+    // normal equations (FP32 Cholesky: the Gram matrix is made of FP32 sums anyway, and
+    // measured iteration counts are the same as with an FP64 factorisation); columns that are
+    // not valid are cut out
+    float A[AA_GRAM_WORDS], r[AA_M];
+    float tr = 0.f;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) {
+        const bool vi = (aa.mask >> i) & 1u;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const bool vj = (aa.mask >> j) & 1u;
+            A[(i * (i + 1)) / 2 + j] = (vi && vj) ? gram[(i * (i + 1)) / 2 + j] : 0.f;
+        }
+        r[i] = vi ? rg[i] : 0.f;
+        tr += A[(i * (i + 1)) / 2 + i];
+    }
+    bool pd = tr > 0.f;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) A[(i * (i + 1)) / 2 + i] += 1e-6f * tr + (((aa.mask >> i) & 1u) ? 0.f : 1.f);
+    // A = L L' in place (L[i][i] holds the RECIPROCAL pivot), then two triangular solves.
+    // All loops have constant bounds with guards, so they unroll completely and A, r
+    // stay in registers.
+#define CVX_TI(i, j) (((i) * ((i) + 1)) / 2 + (j))
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) {
+        float d = A[CVX_TI(j, j)];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k < j) d = fmaf(-A[CVX_TI(j, k)], A[CVX_TI(j, k)], d);
+        pd = pd && (d > 0.f);
+        const float id = f32::cvx_rsqrt(pd ? d : 1.f);
+        A[CVX_TI(j, j)] = id;
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) {
+            if (i <= j) continue;
+            float t = A[CVX_TI(i, j)];
+#pragma unroll
+            for (int k = 0; k < AA_M; ++k)
+                if (k < j) t = fmaf(-A[CVX_TI(i, k)], A[CVX_TI(j, k)], t);
+            A[CVX_TI(i, j)] = t * id;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) {
+        float t = r[i];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k < i) t = fmaf(-A[CVX_TI(i, k)], r[k], t);
+        r[i] = t * A[CVX_TI(i, i)];
+    }
+#pragma unroll
+    for (int ii = 0; ii < AA_M; ++ii) {
+        const int i = AA_M - 1 - ii;
+        float t = r[i];
+#pragma unroll
+        for (int k = 0; k < AA_M; ++k)
+            if (k > i) t = fmaf(-A[CVX_TI(k, i)], r[k], t);
+        r[i] = t * A[CVX_TI(i, i)];
+    }
+#undef CVX_TI
+    bool ok = active && aa.mask != 0u && pd;
+    float fmx = 0.f;
+#pragma unroll
+    for (int j = 0; j < AA_M; ++j) {
+        ok = ok && isfinite(r[j]);
+        fmx = fmaxf(fmx, fabsf(r[j]));
+    }
+    // coefficients as FP16 numbers with a common power-of-two scale fs (max |gamma_j| fs in [0.5, 1))
+    float ifs = 1.f;
+    uint32_t fh[AA_M];
+    {
+        int e = (int)((f2w(fmx) >> 23) & 0xffu) - 126;
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        const float fs = w2f((uint32_t)(127 - e) << 23);
+        ifs = w2f((uint32_t)(127 + e) << 23);
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j) {
+            const float f = (ok && ((aa.mask >> j) & 1u)) ? r[j] * fs : 0.f;
+            fh[j] = pack_h2(f, f);
+        }
+    }
+    H.wait_st();
+
+    // ---- B. extrapolate optimistically: M -= sum_j gamma_j (dM_j + dG_j); remember g_k
+    //         and the step; measure |step| against |g| ---------------------------------
+    float ng = 0.f, ns = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < AA_CHUNKS; ++c) {
+        uint32_t cw[28], gkw[8], spw[4];
+        aa_ld_cols(H, AA_OFF_DS, c, cw);
+        H.wait_ld();
+        float adj[8], stp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) adj[u] = 0.f;
+#pragma unroll
+        for (int j = 0; j < AA_M; ++j)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                adj[2 * w] = hfma_ll(cw[4 * j + w], fh[j], adj[2 * w]);
+                adj[2 * w + 1] = hfma_hl(cw[4 * j + w], fh[j], adj[2 * w + 1]);
+            }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            adj[u] *= ifs;
+            const float gf = active ? (float)G[c * 8 + u] : 0.f;
+            gkw[u] = f2w(gf);
+            stp[u] = gf - adj[u];
+            if (ok) M[c * 8 + u] -= (RT)adj[u];
+            ng = fmaf(gf, gf, ng);
+            ns = fmaf(stp[u], stp[u], ns);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) spw[w] = pack_h2(stp[2 * w] * sc, stp[2 * w + 1] * sc);
+        H.template st<8>(AA_OFF_GP + 8 * c, gkw);
+        H.template st<4>(AA_OFF_SP + 4 * c, spw);
+    }
+    H.wait_st();
+    // ---- C. (rare) the extrapolated step is longer than 10 |g|: undo, keep the plain
+    //         step, drop the history -----------------------------------------------------
+    const bool reject = ok && !(ns <= AA_MAX_STEP2 * ng);
+    if (H.any(reject)) {
+#pragma unroll 1
+        for (int c = 0; c < AA_CHUNKS; ++c) {
+            uint32_t cw[28], gkw[8], spw[4];
+            aa_ld_cols(H, AA_OFF_DS, c, cw);
+            H.template ld<8>(AA_OFF_GP + 8 * c, gkw);
+            H.template ld<4>(AA_OFF_SP + 4 * c, spw);
+            H.wait_ld();
+            float adj[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) adj[u] = 0.f;
+#pragma unroll
+            for (int j = 0; j < AA_M; ++j)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    adj[2 * w] = hfma_ll(cw[4 * j + w], fh[j], adj[2 * w]);
+                    adj[2 * w + 1] = hfma_hl(cw[4 * j + w], fh[j], adj[2 * w + 1]);
+                }
+            if (reject) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) M[c * 8 + u] += (RT)(adj[u] * ifs);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) spw[w] = pack_h2(w2f(gkw[2 * w]) * sc, w2f(gkw[2 * w + 1]) * sc);
+            }
+            H.template st<4>(AA_OFF_SP + 4 * c, spw);
+        }
+        H.wait_st();
+    }
+    if (active && aa.mask != 0u && (!ok || reject)) aa.mask = 0u;
+    aa.have_prev = active;
+    aa.scale_prev = sc;
+}
+
+#if defined(CVX_AA_V1)
+#define aa_step aa_step_v1
+#endif
 
 // ---------------------------------------------------------------------------------
 // 3x3 orthogonal factor  U Vh  of the SVD of a row-major 3x3 matrix (cvxpnpl.py:510-511,

@@ -219,11 +219,21 @@ CVX_HD CVX_REAL jacobi_sweep(ArrT<S, CVX_REAL> T, ArrT<S, CVX_REAL> V)
 // rowk = 1 is the reference's SDP (22 equalities); rowk = 0 is the "rc" ablation of
 // benchmarks/toolkit/methods/rc.py:9-60 (the six row-orthonormality equalities removed).
 // ---------------------------------------------------------------------------------
-// Second half of a DR step: given Z = P_psd(M) in z[] (registers), X = P_aff(2 Z - M - Q/rho),
-// M += alpha (X - Z), G = alpha (X - Z); returns ||X - Z||_F^2.
-template <int S, class QR>
+// Second half of a DR step: given Z = P_psd(M) through the accessor zf(i, j) (i >= j), X = P_aff(2 Z - M - Q/rho),
+// M += alpha (X - Z), G = alpha (X - Z); returns ||X - Z||_F^2.  The accessor is either an array in registers
+// (ZPacked: the full-decomposition solver) or the rank-two form of the tracked solver (ZRank2: two multiply-adds
+// per entry instead of 55 live doubles).
+struct ZPacked {
+    const CVX_REAL* z;
+    CVX_HD CVX_REAL operator()(int i, int j) const { return z[sidx(i, j)]; }
+};
+struct ZRank2 {
+    CVX_REAL a[10], ta[10], b[10], tb[10];   // Z = (t0 a) a' + (t1 b) b'
+    CVX_HD CVX_REAL operator()(int i, int j) const { return fma(ta[i], a[j], tb[i] * b[j]); }
+};
+template <int S, class QR, class ZF>
 CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr, CVX_REAL alpha, CVX_REAL isig, CVX_REAL rowk,
-                                 const CVX_REAL z[55])
+                                 const ZF& zf)
 {
     CVX_REAL res = CVX_REAL(0.0);
     const CVX_REAL inrm9 = CVX_REAL(1.0) / (CVX_REAL(2.0) + isig * isig);
@@ -232,16 +242,17 @@ CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr
     {                                                                                        \
         const int e0 = sidx(i0, j0), e1 = sidx(i1, j1), e2 = sidx(i2, j2);                  \
         const CVX_REAL m0 = M[e0], m1 = M[e1], m2 = M[e2];                                    \
-        const CVX_REAL w0 = CVX_REAL(2.0) * z[e0] - m0 - CVX_Q(i0, j0);                                 \
-        const CVX_REAL w1 = CVX_REAL(2.0) * z[e1] - m1 - CVX_Q(i1, j1);                                 \
-        const CVX_REAL w2 = CVX_REAL(2.0) * z[e2] - m2 - CVX_Q(i2, j2);                                 \
+        const CVX_REAL z0 = zf(i0, j0), z1 = zf(i1, j1), z2 = zf(i2, j2);                     \
+        const CVX_REAL w0 = CVX_REAL(2.0) * z0 - m0 - CVX_Q(i0, j0);                                 \
+        const CVX_REAL w1 = CVX_REAL(2.0) * z1 - m1 - CVX_Q(i1, j1);                                 \
+        const CVX_REAL w2 = CVX_REAL(2.0) * z2 - m2 - CVX_Q(i2, j2);                                 \
         /* third entry on the homogeneous row carries 1/sigma in the scaled problem */      \
         const CVX_REAL a2 = ((i2) == 9) ? (s2) * isig : (CVX_REAL)(s2);                         \
         const CVX_REAL r = ((s0) * w0 + (s1) * w1 + a2 * w2) *                                 \
                          (((i2) == 9) ? inrm9 : ((ROW) ? rowk * (CVX_REAL(1.0) / CVX_REAL(3.0)) : (CVX_REAL(1.0) / CVX_REAL(3.0))));  \
-        const CVX_REAL d0 = w0 - (s0) * r - z[e0];                                            \
-        const CVX_REAL d1 = w1 - (s1) * r - z[e1];                                            \
-        const CVX_REAL d2 = w2 - a2 * r - z[e2];                                              \
+        const CVX_REAL d0 = w0 - (s0) * r - z0;                                               \
+        const CVX_REAL d1 = w1 - (s1) * r - z1;                                               \
+        const CVX_REAL d2 = w2 - a2 * r - z2;                                                 \
         M[e0] = fma(alpha, d0, m0);                                                         \
         M[e1] = fma(alpha, d1, m1);                                                         \
         M[e2] = fma(alpha, d2, m2);                                                         \
@@ -254,11 +265,13 @@ CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr
 #undef CVX_TRI
     // diagonal block
     {
-        CVX_REAL w[9], md[10];
+        CVX_REAL w[9], md[10], zd[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) zd[i] = zf(i, i);
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             md[i] = M[sidx(i, i)];
-            w[i] = CVX_REAL(2.0) * z[sidx(i, i)] - md[i] - qr[sidx(i, i)];
+            w[i] = CVX_REAL(2.0) * zd[i] - md[i] - qr[sidx(i, i)];
         }
         md[9] = M[sidx(9, 9)];
         // D[r][c] = w[3c + r]; project onto unit row sums (over c) and column sums (over r)
@@ -275,12 +288,12 @@ CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr
                 // rowk = 0 ("rc" variant): only the column sums are constrained
                 const CVX_REAL x = w[i] - rowk * (R[r] - CVX_REAL(1.0)) * (CVX_REAL(1.0) / CVX_REAL(3.0)) - (C[c] - CVX_REAL(1.0)) * (CVX_REAL(1.0) / CVX_REAL(3.0))
                                  + rowk * (Gs - CVX_REAL(3.0)) * (CVX_REAL(1.0) / CVX_REAL(9.0));
-                const CVX_REAL d = x - z[sidx(i, i)];
+                const CVX_REAL d = x - zd[i];
                 M[sidx(i, i)] = fma(alpha, d, md[i]);
                 G[sidx(i, i)] = alpha * d;
                 res = fma(d, d, res);
             }
-        const CVX_REAL d9 = CVX_REAL(1.0) / (isig * isig) - z[sidx(9, 9)];
+        const CVX_REAL d9 = CVX_REAL(1.0) / (isig * isig) - zd[9];
         M[sidx(9, 9)] = fma(alpha, d9, md[9]);
         G[sidx(9, 9)] = alpha * d9;
         res = fma(d9, d9, res);
@@ -310,6 +323,6 @@ CVX_HD CVX_REAL dr_step(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> V, ArrT<S, CVX_RE
             }
         }
     }
-    return dr_affine_update(M, G, qr, alpha, isig, rowk, z);
+    return dr_affine_update(M, G, qr, alpha, isig, rowk, ZPacked{z});
 }
 

@@ -19,6 +19,7 @@ struct Opts {
     double aa_on2;    // squared residual below which Anderson acceleration is active
     double rowk;      // 1: reference SDP (22 equalities); 0: "rc" ablation (16 equalities)
     double kappa;     // dual guess of the start point: U0 = kappa Q/rho (see start_decomposition)
+    int early;        // tracked solver: DR iterations run with the full decomposition in the pre-pass (pnpl_track.cuh)
 };
 
 // Default DR parameters (used where the descriptor leaves them 0), measured on seeded
@@ -151,6 +152,7 @@ struct LaneState {
     // (plateau_update; a register the 255-register solver kernel does not have to spare): every
     // `st.phase = ...` clears it.
     bool finite, iterating, converged;
+    int32_t bad;   // tracked solver: consecutive DR iterations whose PSD projection was not certified (pnpl_track.cuh)
     AAState aa;
 };
 
@@ -726,13 +728,15 @@ CVX_HD void problem_park(Arr<S> V, Arr<S> L, const LaneState& st, double* park, 
 // second half of the finish: from the parked state to poses.  V is a strided work
 // array (100) that receives the parked eigenvectors, Qs (45) / Bs (27) receive the
 // re-assembled problem.
-template <int S>
-CVX_HD void extract_parked(const Problem& pr, const Opts& o, const double* park, Arr<S> V, Arr<S> Qs, Arr<S> Bs,
+template <int SV, int S>
+CVX_HD void extract_parked(const Problem& pr, const Opts& o, const double* park, Arr<SV> V, Arr<S> Qs, Arr<S> Bs,
                            double* R_out, double* t_out, double* Z_out, Result& rs)
 {
     double lam[10];
+    if (V.p != park) {
 #pragma unroll 4
-    for (int e = 0; e < 100; ++e) V[e] = park[e];
+        for (int e = 0; e < 100; ++e) V[e] = park[e];
+    }
 #pragma unroll
     for (int j = 0; j < 10; ++j) lam[j] = park[100 + j];
     const double dobj = park[110];

@@ -6,7 +6,7 @@
 // at most two of them from the fifth iteration on (measured on seeded batches, host build:
 // PnPL 8+4 0 of 21 k iterations with three, PnP-8 0.07 %, PnL-6 1.4 %; the first four
 // iterations have up to six).  So:
-//   * the first TRK_EARLY iterations run with the full decomposition in the lane-parallel
+//   * the first iterations (Opts::early, 2 or 4) run with the full decomposition in the lane-parallel
 //     pre-pass kernel (all lanes in the same phase: no divergence);
 //   * from then on a problem carries two orthonormal vectors u0, u1 with Ritz values
 //     th0, th1 -- the positive eigenpairs, or, for a slot whose value is not positive, a
@@ -37,10 +37,18 @@
 
 namespace cvx {
 
+// DR iterations with the full decomposition (pre-pass) before a problem is tracked: Opts::early.  The first iterates
+// have up to six positive eigenvalues.  Hand-backs (host build, 1000 problems each, tolerance 8..12) with 4 / 3 / 2 / 1
+// early iterations: PnPL 8+4 0 / 0 / 0 / 5 %, PnP-8 0.2 / 1.4 / 1.5 / 14 %, PnL-6 4 / 7 / 10 / 50 %: two are enough for
+// the well-constrained point + line problems, four otherwise.
 #ifndef CVX_TRK_EARLY
-#define CVX_TRK_EARLY 4
+#define CVX_TRK_EARLY 0   // > 0: override for experiments
 #endif
-constexpr int TRK_EARLY = CVX_TRK_EARLY;   // DR iterations with the full decomposition (pre-pass)
+CVX_HD int default_early(int n_pts, int n_lines)
+{
+    if (CVX_TRK_EARLY > 0) return CVX_TRK_EARLY;
+    return (n_pts >= 8 && n_lines >= 4) ? 2 : 4;
+}
 
 #if defined(CVX_TRK_DEBUG) && !defined(__CUDA_ARCH__)
 static long g_track_steps = 0, g_track_passes = 0;
@@ -367,10 +375,14 @@ constexpr int TRK_DOUBLES = 126;
 static_assert(TRK_DOUBLES <= PRE_DOUBLES, "the tracked record reuses the pre-pass record");
 
 // Early phase (pre-pass kernel, lane-parallel): assembly has filled rec[0..45]; V receives the start
-// decomposition; run TRK_EARLY plain DR iterations with the full decomposition, then keep the two
+// decomposition; run Opts::early plain DR iterations with the full decomposition, then keep the two
 // largest eigenpairs.  V 100, M 55, T 56, L 10: strided work arrays (shared memory).
+// Returns the third-largest eigenvalue of the iterate the problem is tracked from: the closer it is to zero (or the
+// more positive), the more likely a third positive eigenvalue shows up a few iterations later and the certificate fails
+// (host build: every PnPL 8+4 / PnP-8 problem that was handed back was among the 2 % with the largest value, 60 % of the
+// PnL-6 ones among the top 10 %).  The pre-pass uses it to put those problems at the head of the work queue.
 template <int S>
-CVX_HD void track_early(double* rec, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L)
+CVX_HD double track_early(double* rec, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T, Arr<S> L)
 {
     LaneState st;
     // start_decomposition wrote V (100) and lambda (10) into rec[PRE_V..]; problem_begin copies them in
@@ -380,9 +392,9 @@ CVX_HD void track_early(double* rec, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T
     oe.anderson = false;     // no acceleration, no plateau logic in the first iterations
     if (st.finite) {
 #pragma unroll 1
-        for (int k = 0; k < TRK_EARLY; ++k) {
+        for (int k = 0; k < o.early; ++k) {
             pass_dr(oe, V, M, T, L, GArr{rec, 1}, st);
-            if (!st.iterating) break;      // converged / capped already (max_iters < TRK_EARLY)
+            if (!st.iterating) break;      // converged / capped already (max_iters < early)
             pass_eig(oe, V, M, T, L, GArr{rec, 1}, st);
         }
     }
@@ -395,9 +407,23 @@ CVX_HD void track_early(double* rec, const Opts& o, Arr<S> V, Arr<S> M, Arr<S> T
     rec[TR_TH] = th[0];
     rec[TR_TH + 1] = th[1];
     rec[TR_IT] = (double)st.it;
-    // bit 0: the DR loop is over already (converged within the early iterations or max_iters <= TRK_EARLY);
+    // bit 0: the DR loop is over already (converged within the early iterations or max_iters <= early);
     // bit 1: converged
     rec[TR_FLAGS] = (double)((st.iterating ? 0 : 1) | (st.converged ? 2 : 0));
+    // third largest eigenvalue
+    double a0 = -1e300, a1 = -1e300, a2 = -1e300;
+#pragma unroll 1
+    for (int j = 0; j < 10; ++j) {
+        const double l = L[j];
+        if (l > a0) {
+            a2 = a1; a1 = a0; a0 = l;
+        } else if (l > a1) {
+            a2 = a1; a1 = l;
+        } else if (l > a2) {
+            a2 = l;
+        }
+    }
+    return a2;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -441,6 +467,7 @@ CVX_HD void track_begin(const double* rec, const Opts& o, Arr<S> M, Arr<S> U, Ar
     st.finite = isfinite(rho);
     st.iterating = st.finite && !(fl & 1);
     st.converged = (fl & 2) != 0;
+    st.bad = 0;
     if (st.finite && !st.iterating) st.phase = 1;
 }
 
@@ -469,6 +496,7 @@ CVX_HD void track_begin_warm(const double* rec, const double* w, const Opts& o, 
     st.finite = isfinite(rho);
     st.iterating = st.finite && st.it < o.max_iters;
     st.converged = false;
+    st.bad = 0;
     if (st.finite && !st.iterating) st.phase = 1;
 }
 
@@ -477,14 +505,23 @@ template <int S>
 CVX_HD bool track_pass_dr(const Opts& o, Arr<S> M, Arr<S> G, Arr<S> U, Arr<S> TH, Arr<S> QR, LaneState& st)
 {
     if (!st.finite || !st.iterating) return false;
-    double z[55];
-    track_psd(U, TH, z);
-    const double res = dr_affine_update(M, G, QR, o.alpha, 1.0 / o.sigma, o.rowk, z);
+    ZRank2 zf;
+    {
+        const double t0 = fmax(TH[0], 0.0), t1 = fmax(TH[1], 0.0);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            zf.a[i] = U[i];
+            zf.b[i] = U[10 + i];
+            zf.ta[i] = t0 * zf.a[i];
+            zf.tb[i] = t1 * zf.b[i];
+        }
+    }
+    const double res = dr_affine_update(M, G, QR, o.alpha, 1.0 / o.sigma, o.rowk, zf);
     ++st.it;
 #if defined(CVX_TRACE) && !defined(__CUDA_ARCH__)
     printf("trk it %d res %.3e aa_mask %u th %.4e %.4e\n", st.it, sqrt(res), st.aa.mask, (double)TH[0], (double)TH[1]);
 #endif
-    if (!(res > o.eps2)) {  // also leaves on NaN
+    if (!(res > o.eps2) && (st.bad == 0 || !(res <= o.eps2))) {  // also leaves on NaN; never converges on an uncertified projection
         st.converged = (res <= o.eps2);
         st.iterating = false;
         st.phase = 1;
@@ -496,6 +533,11 @@ CVX_HD bool track_pass_dr(const Opts& o, Arr<S> M, Arr<S> G, Arr<S> U, Arr<S> TH
         return false;
     }
     if (!o.anderson) return false;
+    if (st.bad > 0) {   // the step came from an uncertified projection: keep it out of the accelerator and the plateau detector
+        aa_reset(st.aa);
+        st.res_prev = 1e300;
+        return false;
+    }
     {
         const int tau = plateau_update(st.phase, res, st.res_prev);
         if (tau > 0) {
@@ -540,7 +582,19 @@ CVX_HD int track_pass_eig(const Opts& o, Arr<S> M, Arr<S> U, Arr<S> TH, Arr<S> B
         rc = track_step(M, U, TH, BS, corr2, any);
         if (!(rc != TRK_OK && corr2 > CVX_TRK_REPEAT2)) break;
     }
-    if (rc != TRK_OK) return -1;
+#ifndef CVX_TRK_TOLERATE
+#define CVX_TRK_TOLERATE 8   // hand-backs, host build, 1000 problems each, 0 / 4 / 8 / 16: PnP-8 1.2 / 0.7 / 0.2 / 0.1 %, PnL-6 6.8 / 5.2 / 4.1 / 3.8 %
+#endif
+    if (rc != TRK_OK) {
+        // A third positive eigenvalue is usually a transient of the first 10-20 iterations (host build: 92 % of the
+        // failed certificates; median iteration 11).  Any M is a valid DR state, so the problem may go on with the
+        // two tracked pairs -- an inexact projection -- for up to CVX_TRK_TOLERATE iterations, out of the accelerator's
+        // sight and unable to converge, before it is handed back.
+        if (!st.iterating || st.bad >= CVX_TRK_TOLERATE || !isfinite(corr2)) return -1;
+        ++st.bad;
+    } else {
+        st.bad = 0;
+    }
     if (st.iterating) {
         const double rf = rescale_factor(st.it);
         if (rf > 0.0) {

@@ -135,6 +135,85 @@ __device__ __forceinline__ void round_pair(int r, int k, int& p, int& q)
     q = a < b ? b : a;
 }
 
+// Pivot pairs of a lane's work items for all nine rounds of a sweep, four bits each:
+// T block (pa, qa) x (pb, qb); V items rows lane / 5 (pair pb, qb) and (lane + 32) / 5 (pair p1, q1)
+__device__ __forceinline__ void sweep_tables(int lane, uint32_t pk[9])
+{
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        int pa, qa, pb, qb, p1, q1;
+        round_pair(r, lane < 25 ? lane / 5 : 0, pa, qa);
+        round_pair(r, lane % 5, pb, qb);
+        round_pair(r, (lane + 32) % 5, p1, q1);
+        pk[r] = (uint32_t)pa | ((uint32_t)qa << 4) | ((uint32_t)pb << 8) | ((uint32_t)qb << 12) | ((uint32_t)p1 << 16) |
+                ((uint32_t)q1 << 20);
+    }
+}
+
+// One Jacobi sweep on S.T (full form) accumulating the rotations into S.V: 9 rounds of 5 disjoint rotations.
+// Round: lanes 0..4 compute (c, s); then 25 lanes update one 2x2 block of T each (T' = J'TJ, blocks are
+// disjoint -> in place) and all lanes rotate rows of V.
+__device__ __forceinline__ void warp_sweep(WarpSmem& S, int lane, const uint32_t pk[9])
+{
+    const int ka = lane < 25 ? lane / 5 : 0, kb = lane % 5, k1 = (lane + 32) % 5;
+    const int i0 = lane / 5, i1 = (lane + 32) / 5;
+#pragma unroll 1   // rolled: measured faster than nine unrolled copies (pk then lives in local memory)
+    for (int round = 0; round < 9; ++round) {
+        const int pa = pk[round] & 15, qa = (pk[round] >> 4) & 15, pb = (pk[round] >> 8) & 15,
+                  qb = (pk[round] >> 12) & 15, p1 = (pk[round] >> 16) & 15, q1 = (pk[round] >> 20) & 15;
+        if (lane < 5) {
+            // lane k < 5 owns pair k = (pb, qb)
+            double c, s;
+            jacobi_cs_fast(S.T[pb * 11], S.T[qb * 11], S.T[qb * 10 + pb], c, s);
+            S.cs[2 * lane] = c;
+            S.cs[2 * lane + 1] = s;
+        }
+        __syncwarp();
+        const double cb = S.cs[2 * kb], sb = S.cs[2 * kb + 1];
+        if (lane < 25) {
+            const double ca = S.cs[2 * ka], sa = S.cs[2 * ka + 1];
+            const double b00 = S.T[pa * 10 + pb], b01 = S.T[pa * 10 + qb], b10 = S.T[qa * 10 + pb],
+                         b11 = S.T[qa * 10 + qb];
+            const double y00 = ca * b00 - sa * b10, y01 = ca * b01 - sa * b11;
+            const double y10 = sa * b00 + ca * b10, y11 = sa * b01 + ca * b11;
+            const bool dg = ka == kb;   // the pivot itself is annihilated exactly
+            S.T[pa * 10 + pb] = y00 * cb - y01 * sb;
+            S.T[pa * 10 + qb] = dg ? 0.0 : y00 * sb + y01 * cb;
+            S.T[qa * 10 + pb] = dg ? 0.0 : y10 * cb - y11 * sb;
+            S.T[qa * 10 + qb] = y10 * sb + y11 * cb;
+        }
+        {
+            const double vp = S.V[i0 * 10 + pb], vq = S.V[i0 * 10 + qb];
+            S.V[i0 * 10 + pb] = fma(cb, vp, -sb * vq);
+            S.V[i0 * 10 + qb] = fma(sb, vp, cb * vq);
+        }
+        if (lane < 18) {
+            const double c = S.cs[2 * k1], s = S.cs[2 * k1 + 1];
+            const double vp = S.V[i1 * 10 + p1], vq = S.V[i1 * 10 + q1];
+            S.V[i1 * 10 + p1] = fma(c, vp, -s * vq);
+            S.V[i1 * 10 + q1] = fma(s, vp, c * vq);
+        }
+        __syncwarp();
+    }
+}
+
+// Cold eigen-decomposition of S.M (full form) by one warp: V = I, T = M, cyclic sweeps.  The rotations annihilate a
+// pivot to ~1e-7 of its size (jacobi_cs_fast), so the off-diagonal part shrinks at least that fast per sweep once the
+// quadratic phase is over; ten sweeps leave it far below what the solver's own per-iteration sweep / the polishing
+// passes of the thread solver expect as a warm start.
+__device__ __forceinline__ void warp_cold_decompose(WarpSmem& S, int lane, const uint32_t pk[9])
+{
+    for (int e = lane; e < 100; e += 32) {
+        S.T[e] = S.M[e];
+        S.V[e] = (e / 10 == e % 10) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int sw = 0; sw < 10; ++sw) warp_sweep(S, lane, pk);
+    if (lane < 10) S.L[lane] = S.T[lane * 11];
+    __syncwarp();
+}
+
 // Normal equations of the Anderson step: packed Gram matrix (lower), right-hand side,
 // valid-column mask -> coefficients.  Same arithmetic as aa_step.
 __device__ __forceinline__ bool aa_solve_packed(const float* gram, const float* rg, uint32_t mask, float f[AA_M])
@@ -200,9 +279,10 @@ __device__ __forceinline__ bool aa_solve_packed(const float* gram, const float* 
 }
 
 // DR iterations of one problem by one warp.  S holds M, V, L, Q (= Q/rho, full form
-// with a zero last row/column); `it` continues the problem's iteration count.
+// with a zero last row/column); `it` continues the problem's iteration count; the loop ends on
+// convergence or at iteration it_stop (<= o.max_iters).
 __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, int& it, bool& converged,
-                                          double& rho)
+                                          double& rho, int it_stop)
 {
     const unsigned FULL = 0xffffffffu;
     const double isig = 1.0 / o.sigma, inrm9 = 1.0 / (2.0 + isig * isig);
@@ -211,20 +291,8 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
     unpack_idx(lane, er[0], ec[0]);
     unpack_idx(lane + 32 < 55 ? lane + 32 : 0, er[1], ec[1]);
     const int np = lane + 32 < 55 ? 2 : 1;
-    // pivot pairs of this lane's work items, all nine rounds, four bits each:
-    // T block (pa, qa) x (pb, qb); V items rows lane / 5 (pair pb, qb) and (lane + 32) / 5 (pair p1, q1)
     uint32_t pk[9];
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-        int pa, qa, pb, qb, p1, q1;
-        round_pair(r, lane < 25 ? lane / 5 : 0, pa, qa);
-        round_pair(r, lane % 5, pb, qb);
-        round_pair(r, (lane + 32) % 5, p1, q1);
-        pk[r] = (uint32_t)pa | ((uint32_t)qa << 4) | ((uint32_t)pb << 8) | ((uint32_t)qb << 12) | ((uint32_t)p1 << 16) |
-                ((uint32_t)q1 << 20);
-    }
-    const int ka = lane < 25 ? lane / 5 : 0, kb = lane % 5, k1 = (lane + 32) % 5;
-    const int i0 = lane / 5, i1 = (lane + 32) / 5;
+    sweep_tables(lane, pk);
     uint32_t mask = 0u;
     bool have_prev = false;
     int wslot = 0;
@@ -311,7 +379,7 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
             converged = (res <= o.eps2);
             break;
         }
-        if (it >= o.max_iters) break;
+        if (it >= it_stop) break;   // o.max_iters, or earlier when the caller only lends the warp for a while
         __syncwarp();
         // ---- 4. Anderson acceleration in the tail (same rules as pass_dr / aa_step) ------
         // plateau jump (same rule as pass_dr: plateau_update); Z holds the step g
@@ -419,47 +487,8 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
             S.T[c * 10 + r] = s;
         }
         __syncwarp();
-        // ---- 6. one Jacobi sweep: 9 rounds of 5 disjoint rotations.  Round: lanes 0..4
-        //         compute (c, s); then 25 lanes update one 2x2 block of T each
-        //         (T' = J'TJ, blocks are disjoint -> in place) and all lanes rotate rows of V.
-#pragma unroll 1   // rolled: measured faster than nine unrolled copies (pk then lives in local memory)
-        for (int round = 0; round < 9; ++round) {
-            const int pa = pk[round] & 15, qa = (pk[round] >> 4) & 15, pb = (pk[round] >> 8) & 15,
-                      qb = (pk[round] >> 12) & 15, p1 = (pk[round] >> 16) & 15, q1 = (pk[round] >> 20) & 15;
-            if (lane < 5) {
-                // lane k < 5 owns pair k = (pb, qb)
-                double c, s;
-                jacobi_cs_fast(S.T[pb * 11], S.T[qb * 11], S.T[qb * 10 + pb], c, s);
-                S.cs[2 * lane] = c;
-                S.cs[2 * lane + 1] = s;
-            }
-            __syncwarp();
-            const double cb = S.cs[2 * kb], sb = S.cs[2 * kb + 1];
-            if (lane < 25) {
-                const double ca = S.cs[2 * ka], sa = S.cs[2 * ka + 1];
-                const double b00 = S.T[pa * 10 + pb], b01 = S.T[pa * 10 + qb], b10 = S.T[qa * 10 + pb],
-                             b11 = S.T[qa * 10 + qb];
-                const double y00 = ca * b00 - sa * b10, y01 = ca * b01 - sa * b11;
-                const double y10 = sa * b00 + ca * b10, y11 = sa * b01 + ca * b11;
-                const bool dg = ka == kb;   // the pivot itself is annihilated exactly
-                S.T[pa * 10 + pb] = y00 * cb - y01 * sb;
-                S.T[pa * 10 + qb] = dg ? 0.0 : y00 * sb + y01 * cb;
-                S.T[qa * 10 + pb] = dg ? 0.0 : y10 * cb - y11 * sb;
-                S.T[qa * 10 + qb] = y10 * sb + y11 * cb;
-            }
-            {
-                const double vp = S.V[i0 * 10 + pb], vq = S.V[i0 * 10 + qb];
-                S.V[i0 * 10 + pb] = fma(cb, vp, -sb * vq);
-                S.V[i0 * 10 + qb] = fma(sb, vp, cb * vq);
-            }
-            if (lane < 18) {
-                const double c = S.cs[2 * k1], s = S.cs[2 * k1 + 1];
-                const double vp = S.V[i1 * 10 + p1], vq = S.V[i1 * 10 + q1];
-                S.V[i1 * 10 + p1] = fma(c, vp, -s * vq);
-                S.V[i1 * 10 + q1] = fma(s, vp, c * vq);
-            }
-            __syncwarp();
-        }
+        // ---- 6. one Jacobi sweep (warp_sweep) ----------------------------------------------------
+        warp_sweep(S, lane, pk);
         if (lane < 10) S.L[lane] = S.T[lane * 11];
         __syncwarp();
         // ---- 7. slow problem: continue with a smaller penalty, once (rescale_rho) ---------

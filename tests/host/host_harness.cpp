@@ -9,8 +9,10 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdio>
 #include "../../cvxpnpl_b200/csrc/pnpl_solve.cuh"
 #include "../../cvxpnpl_b200/csrc/pnpl_track.cuh"
+#include <cstdio>
 
 extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
                           const double* pts_2d, const double* pts_3d, const double* line_2d,
@@ -29,6 +31,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
     o.anderson = anderson != 0;
     o.rowk = variant == 1 ? 0.0 : 1.0;
     o.kappa = cvx::DUAL_GUESS;
+    o.early = cvx::default_early(n_pts, n_lines);
     o.aa_on2 = (anderson > 1) ? (1e-3 * anderson) * (1e-3 * anderson) : cvx::AA_RES2_ON;   // test hook: threshold in 1e-3 units
     std::vector<double> V(100), M(56), T(56), L(10), qr(45);   // T[55] = 0: zero pad for aa_step
     std::vector<uint32_t> hist(cvx::AA_WORDS, 0u);
@@ -118,7 +121,7 @@ extern "C" int host_plateau_update(int32_t* plat, double res2, double res2_prev)
 
 
 // The tracked solver (pnpl_track.cuh) exactly as the CUDA kernels chain it: pre-pass (assembly, start
-// decomposition, TRK_EARLY full iterations) -> tracked DR loop with Anderson steps -> park -> extraction.
+// decomposition, Opts::early full iterations) -> tracked DR loop with Anderson steps -> park -> extraction.
 // A problem whose certificate fails continues like the warp-per-problem kernel does: cold full
 // decomposition of its M, full-decomposition DR loop.  fallbacks[b] = 1 for those.
 extern "C" int host_solve_track(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
@@ -139,6 +142,7 @@ extern "C" int host_solve_track(int64_t B, int n_pts, int n_lines, const double*
     o.rowk = variant == 1 ? 0.0 : 1.0;
     o.kappa = cvx::DUAL_GUESS;
     o.aa_on2 = cvx::AA_RES2_ON;
+    o.early = cvx::default_early(n_pts, n_lines);
     std::vector<double> V(100), M(56), T(56), L(10), qr(45), U(20), TH(2), BS(36), Qs(45), Bs(27);
     std::vector<uint32_t> hist(cvx::AA_WORDS, 0u);
     const cvx::AnyLane any;
@@ -172,6 +176,18 @@ extern "C" int host_solve_track(int64_t B, int n_pts, int n_lines, const double*
             if (rc > 0) break;
             if (rc < 0) {
                 handed = true;
+#if defined(CVX_FAIL_TRACE)
+                {
+                    double tt[55], vv[100];
+                    for (int e = 0; e < 55; ++e) tt[e] = M[e];
+                    for (int i = 0; i < 100; ++i) vv[i] = (i / 10 == i % 10);
+                    for (int sw = 0; sw < 12; ++sw) cvx::jacobi_sweep(cvx::Arr<1>{tt}, cvx::Arr<1>{vv});
+                    double ev[10];
+                    for (int j = 0; j < 10; ++j) ev[j] = tt[cvx::sidx(j, j)];
+                    for (int a = 0; a < 10; ++a) for (int b2 = a + 1; b2 < 10; ++b2) if (ev[b2] > ev[a]) { double x = ev[a]; ev[a] = ev[b2]; ev[b2] = x; }
+                    printf("FAIL b %ld it %d iterating %d res %.2e ev %.3e %.3e %.3e %.3e th %.3e %.3e\n", (long)b, st.it, (int)st.iterating, sqrt(st.res_prev), ev[0], ev[1], ev[2], ev[3], TH[0], TH[1]);
+                }
+#endif
                 break;
             }
         }
