@@ -208,11 +208,7 @@ enum {
     CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3, CTRL_NEXT32 = 4, CTRL_ACTIVE = 5,
     CTRL_NFAIL = 6,      // problems the tracked solver handed back (failed certificate / stragglers): length of fail_list
     CTRL_FAIL_NEXT = 7,  // queue head of the full-decomposition solver working on that list
-    CTRL_TRK_NEXT = 8,   // queue head of the tracked solver
-    CTRL_TRK_DONE = 9,   // CTAs of the tracked solver whose worker warps have finished
-    CTRL_SVC_NEXT = 10,  // tickets taken by the service warps of the tracked solver (entries of fail_list)
-    CTRL_NRISKY = 11,    // length of the "risky first" list at the head of the tracked solver's queue
-    CTRL_RISK_BIN = 12   // risk bin from which a problem is on that list
+    CTRL_TRK_NEXT = 8    // queue head of the tracked solver
 };
 
 // RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
@@ -344,142 +340,37 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
 }
 
 // ---------------------------------------------------------------------------------
-// Tracked persistent solver (pnpl_track.cuh), warp-specialised: one CTA per SM, 256 threads.
-//
-// Warps 0-3, the WORKERS: same structure as solve_fused_kernel<false> -- one thread per problem, 128 problems per
-// CTA, lane-level work stealing from a difficulty-ordered queue, Anderson history in tensor memory -- but the PSD
-// projection comes from two tracked eigenpairs refined once per iteration instead of a full 10x10 decomposition.
-// Per-problem shared memory: M 55 | G 56 (the step; its first 36 words double as the Cholesky scratch of track_step
-// between the Anderson step and the next DR step) | U 20 | TH 2 | Q/rho 45 = 178 doubles.  The four worker warps meet
-// at a named barrier every pass (see below: they share instruction-cache lines).
-//
+// Tracked persistent solver (pnpl_track.cuh): same structure as solve_fused_kernel<false> -- one thread per problem,
+// 128 problems per CTA, one CTA per SM, lane-level work stealing from a difficulty-ordered queue, Anderson history in
+// tensor memory -- but the PSD projection comes from two tracked eigenpairs refined once per iteration instead of a
+// full 10x10 decomposition.  Per-problem shared memory: M 55 | G 56 (the step; its first 36 words double as the
+// Cholesky scratch of track_step between the Anderson step and the next DR step) | U 20 | TH 2 | Q/rho 45 = 178
+// doubles.  The four warps meet at a barrier every pass (they share instruction-cache lines, see below).
 // A problem whose certificate fails for good (a third positive eigenvalue that stays, or a slot that lost its
 // vector), and a straggler still iterating `grace` passes after the queue ran dry, goes back into its pre-pass record
-// and onto fail_list.
-//
-// Warps 4-7, the SERVICE warps: one warp per handed-back problem, CONCURRENTLY with the workers (which use a quarter
-// of the SM's issue slots).  A service warp takes a ticket, waits until that entry of fail_list is published (or the
-// workers of every CTA are done), decomposes the problem's iterate from scratch (warp-cooperative cyclic Jacobi) and
-// runs the warp-per-problem DR loop of pnpl_warp.cuh to the end; the result goes into the problem's WARM record with
-// the "DR loop over" flag, and solve_fused_kernel<false>(from_track) polishes and parks it like any other.  Only the
-// first `svc_max` entries are served this way: a family that hands back a large part of the batch (minimal problems)
-// is better off in the throughput-optimal thread mapping, so the rest of the list goes through redecomp_kernel and the
-// full-decomposition solver after this kernel, as before.
+// and onto fail_list: redecomp_kernel + solve_fused_kernel<false>(from_track) finish those with the full
+// decomposition.
+// (Tried and dropped, profiles/README.md r2h-r2j: four more warps per CTA that serve the handed-back problems
+// concurrently, warp per problem.  Their 36 KB of shared memory shrink the L1 from 45 to 9 KB, the kernel's ~100
+// register spills per pass then miss, and the bulk got 0.85 ms slower -- more than the 0.5 ms tail it hides.)
 // ---------------------------------------------------------------------------------
 constexpr int TRK_SMEM_DOUBLES = 55 + 56 + 20 + 2 + 45;
-constexpr int NT_TRK = 2 * NT;            // worker + service warps
-constexpr int N_SVC_WARPS = NT / 32;
-constexpr int SVC_ITERS = 400;
-constexpr size_t SMEM_TRK_BYTES = (size_t)NT * TRK_SMEM_DOUBLES * sizeof(double) + N_SVC_WARPS * sizeof(cvx::WarpSmem);
-
-// barrier among the worker warps only (named barrier 1), with an AND vote
-__device__ __forceinline__ bool workers_sync_and(bool pred)
-{
-    uint32_t r;
-    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; barrier.cta.red.and.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(r) : "r"((uint32_t)pred), "n"(NT) : "memory");
-    return r != 0;
-}
-
-__device__ __forceinline__ void service_loop(cvx::WarpSmem& S, const Opts& o, unsigned long long* ctrl,
-                                             const int32_t* fail_list, double* pre, double* warm, unsigned n_ctas,
-                                             unsigned long long svc_max)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    uint32_t pk[9];
-    cvx::sweep_tables(lane, pk);
-    for (;;) {
-        unsigned long long k = 0;
-        if (lane == 0) k = atomicAdd(ctrl + CTRL_SVC_NEXT, 1ULL);
-        k = __shfl_sync(FULL, k, 0);
-        if (k >= svc_max) break;
-        // wait until entry k is published (fail_list is initialised to -1), or until no worker is left to publish it
-        int b = -1;
-        for (;;) {
-            int done = 0;
-            if (lane == 0) {
-                b = *(volatile const int32_t*)(fail_list + k);
-                if (b < 0 && *(volatile unsigned long long*)(ctrl + CTRL_TRK_DONE) >= (unsigned long long)n_ctas) {
-                    __threadfence();
-                    b = *(volatile const int32_t*)(fail_list + k);   // published just before the last CTA finished?
-                    done = 1;
-                }
-            }
-            b = __shfl_sync(FULL, b, 0);
-            done = __shfl_sync(FULL, done, 0);
-            if (b >= 0 || done) break;
-            __nanosleep(2000);
-        }
-        if (b < 0) break;
-        __threadfence();
-        double* rec = pre + (int64_t)b * cvx::PRE_DOUBLES;   // written by a worker of some SM: read past L1
-        for (int e = lane; e < 100; e += 32) {
-            const int r = e / 10, c = e - 10 * r;
-            S.M[e] = __ldcg(rec + cvx::TR_M + cvx::sidx(r, c));
-            S.Q[e] = (r < 9 && c < 9) ? __ldcg(rec + cvx::TR_Q + cvx::sidx(r, c)) : 0.0;
-        }
-        for (int e = lane; e < 56; e += 32) {
-            S.gp[e] = S.sp[e] = S.gk[e] = 0.f;
-#pragma unroll
-            for (int j = 0; j < cvx::AA_M; ++j) S.dG[j][e] = S.dS[j][e] = 0.f;
-        }
-        if (lane < cvx::AA_GRAM_WORDS) S.gram[lane] = 0.f;
-        if (lane < 16) S.dots[lane] = 0.f;
-        int it = (int)__ldcg(rec + cvx::TR_IT);
-        double rho = __ldcg(rec + cvx::TR_RHO);
-        const int fl = (int)__ldcg(rec + cvx::TR_FLAGS);
-        __syncwarp();
-        cvx::warp_cold_decompose(S, lane, pk);
-        bool converged = (fl & 2) != 0;
-        // a service warp is lent to a problem for at most SVC_ITERS iterations: a problem that needs more (the
-        // batch's few cap runners) goes on in the kernels after this one, where the whole GPU is free for them
-        bool over = (fl & 1) != 0;
-        if (!over) {
-            const int stop = it + SVC_ITERS < o.max_iters ? it + SVC_ITERS : o.max_iters;
-            cvx::warp_dr_loop(S, o, lane, it, converged, rho, stop);
-            over = converged || it >= o.max_iters;
-        }
-        double* w = warm + (int64_t)b * cvx::WARM_DOUBLES;
-        for (int p = lane; p < 55; p += 32) {
-            int r, c;
-            cvx::unpack_idx(p, r, c);
-            w[p] = S.M[r * 10 + c];
-            if (r < 9) rec[cvx::TR_Q + p] = S.Q[r * 10 + c];   // Q / rho changes with a penalty rescale
-        }
-        for (int e = lane; e < 100; e += 32) w[55 + e] = S.V[e];
-        if (lane < 10) w[155 + lane] = S.L[lane];
-        if (lane == 0) {
-            w[165] = (double)it;
-            rec[cvx::TR_RHO] = rho;
-            rec[cvx::TR_IT] = (double)it;
-            rec[cvx::TR_FLAGS] = (double)((over ? 1 : 0) | (converged ? 2 : 0));   // DR loop over: only polish + park
-        }
-        __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(NT_TRK, 1)
-solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double* pre, double* park, double* warm_out,
-                   const double* warm, const int32_t* order, const int32_t* risky, const unsigned char* bucket_of,
-                   unsigned risky_cap, int32_t* fail_list, int grace, int handoff_max, unsigned long long svc_max)
+constexpr size_t SMEM_TRK_BYTES = (size_t)NT * TRK_SMEM_DOUBLES * sizeof(double);
+__global__ void __launch_bounds__(NT, 1)
+solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double* pre, double* park, const double* warm,
+                   const int32_t* order, int32_t* fail_list, int grace, int handoff_max)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
-    __shared__ int queue_dry;   // some lane of this CTA has seen the work queue empty (the workers meet at a barrier every pass)
+    __shared__ int queue_dry;   // some lane of this CTA has seen the work queue empty (the lanes meet at a barrier every pass)
     const int tid = threadIdx.x;
     if (tid == 0) queue_dry = 0;
-    const uint32_t tmem_base = tmem_alloc_all(&tmem_slot);   // (CTA-wide barrier inside)
-    if (tid >= NT) {
-        cvx::WarpSmem* ws = reinterpret_cast<cvx::WarpSmem*>(smem + (size_t)NT * TRK_SMEM_DOUBLES);
-        service_loop(ws[(tid - NT) >> 5], o, ctrl, fail_list, pre, warm_out, gridDim.x, svc_max);
-        return;
-    }
     cvx::Arr<NT> M{smem + tid};
     cvx::Arr<NT> G{smem + (size_t)55 * NT + tid};
     cvx::Arr<NT> U{smem + (size_t)111 * NT + tid};
     cvx::Arr<NT> TH{smem + (size_t)131 * NT + tid};
     cvx::Arr<NT> QR{smem + (size_t)133 * NT + tid};
+    const uint32_t tmem_base = tmem_alloc_all(&tmem_slot);
     const HistTmem H{tmem_base + ((uint32_t)((tid >> 5) & 3) << 21)};
     {
         uint32_t zero[32];
@@ -494,11 +385,7 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
     bool exhausted = false;
     int drain = 0;
     bool counted = false;
-    // queue positions: first the "risky first" list (problems likely to be handed back: their service then runs under
-    // the bulk of the batch instead of behind it), then the difficulty-ordered batch, minus the ones already taken
-    const unsigned long long n_risky_raw = ctrl[CTRL_NRISKY];
-    const unsigned long long n_risky = n_risky_raw < risky_cap ? n_risky_raw : risky_cap;
-    const unsigned long long n_work = n_risky + (unsigned long long)d.batch;
+    const unsigned long long n_work = (unsigned long long)d.batch;
     cvx::LaneState st;
     st.finite = false;
     st.iterating = false;
@@ -513,33 +400,23 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
     int wslot = 0;
     for (;;) {
         if (b < 0 && !exhausted) {
-            for (;;) {
-                const unsigned long long nb = atomicAdd(ctrl + CTRL_TRK_NEXT, 1ULL);
-                if (nb >= n_work) {
-                    exhausted = true;
-                    queue_dry = 1;
-                    break;
-                }
-                if (nb < n_risky) {
-                    b = (int64_t)risky[nb];
-                    break;
-                }
-                b = (int64_t)order[nb - n_risky];
-                if (!(bucket_of[b] & 0x80)) break;   // (else: it was on the risky list)
-                b = -1;
-            }
-            if (b >= 0) {
+            const unsigned long long nb = atomicAdd(ctrl + CTRL_TRK_NEXT, 1ULL);
+            if (nb < n_work) {
+                b = (int64_t)order[nb];
                 if (warm)
                     cvx::track_begin_warm(pre + b * cvx::PRE_DOUBLES, warm + b * cvx::WARM_DOUBLES, o, M, U, TH, QR, st);
                 else
                     cvx::track_begin(pre + b * cvx::PRE_DOUBLES, o, M, U, TH, QR, st);
+            } else {
+                exhausted = true;
+                queue_dry = 1;
             }
         }
-        // The four worker warps start every pass together: they then walk the same (mostly straight-line, ~100 KB)
-        // instruction stream and share the lines one of them brought into the SM's instruction cache.  ncu,
-        // free-running warps: stall_no_instruction 1.6 cycles per issued instruction (every warp streams the loop
-        // body from L2: 3.8 TB/s of instruction fetch over the chip); in lock-step 0.08, kernel 5.07 -> 4.53 ms.
-        if (workers_sync_and(b < 0)) break;
+        // The four warps of the CTA start every pass together: they then walk the same (mostly straight-line,
+        // ~100 KB) instruction stream and share the lines one of them brought into the SM's instruction cache.
+        // ncu, free-running warps: stall_no_instruction 1.6 cycles per issued instruction (every warp streams the
+        // loop body from L2: 3.8 TB/s of instruction fetch over the chip); in lock-step 0.08, kernel 5.07 -> 4.53 ms.
+        if (__syncthreads_and(b < 0)) break;
         bool give_up = false;
         if (grace >= 0 && b >= 0 && st.iterating) {
             if (drain > 0 || *(volatile int*)&queue_dry) {
@@ -562,11 +439,8 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
                 cvx::track_park(o, U, TH, st, park + b * cvx::PARK_DOUBLES, d.iters + b);
                 b = -1;
             } else if (rc < 0) {
-                // record first, then the list entry a service warp may be waiting for
                 cvx::track_handoff(M, QR, st, pre + b * cvx::PRE_DOUBLES);
-                __threadfence();
-                *(volatile int32_t*)(fail_list + atomicAdd(ctrl + CTRL_NFAIL, 1ULL)) = (int32_t)b;
-                __threadfence();
+                fail_list[atomicAdd(ctrl + CTRL_NFAIL, 1ULL)] = (int32_t)b;
                 b = -1;
                 if (give_up) exhausted = true;
             }
@@ -576,28 +450,19 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
             }
         }
     }
-    // workers done: tell the service warps (of every CTA), release the tensor memory
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    workers_sync_and(true);
-    if (tid == 0) {
-        __threadfence();
-        atomicAdd(ctrl + CTRL_TRK_DONE, 1ULL);
-    }
-    if (tid < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    tmem_free_all(tmem_base);
 }
 
-// Problems handed back by the tracked solver that its service warps did not take (entries `first`... of the list):
-// cold eigen-decomposition of their DR iterate M (cyclic Jacobi, lane-parallel), exported in the WARM format the
-// full-decomposition solver starts from.
+// Problems handed back by the tracked solver: cold eigen-decomposition of their DR iterate M (cyclic Jacobi,
+// lane-parallel), exported in the WARM format the full-decomposition solver starts from.
 constexpr int NT_R = 64;
 constexpr size_t SMEM_R_BYTES = (size_t)NT_R * 100 * sizeof(double);
 __global__ void __launch_bounds__(NT_R) redecomp_kernel(const unsigned long long* ctrl, const int32_t* fail_list,
-                                                        const double* pre, double* warm, unsigned long long first)
+                                                        const double* pre, double* warm)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
-    for (unsigned long long k = first + (unsigned long long)blockIdx.x * NT_R + tid; k < ctrl[CTRL_NFAIL];
+    for (unsigned long long k = (unsigned long long)blockIdx.x * NT_R + tid; k < ctrl[CTRL_NFAIL];
          k += (unsigned long long)gridDim.x * NT_R) {
     const int64_t b = fail_list[k];
     const double* rec = pre + b * cvx::PRE_DOUBLES;
@@ -784,19 +649,9 @@ __device__ __forceinline__ int difficulty_bucket(const double* rec, const Opts& 
 
 // EARLY: also run the first Opts::early DR iterations with the full decomposition (all lanes in the same phase) and
 // leave the record in the tracked solver's format (pnpl_track.cuh).
-// Risk of a failed certificate (third eigenvalue after the early iterations, see track_early) as a histogram bin:
-// 1/16 steps over [-8, 8).
-constexpr int N_RISK_BINS = 256;
-__device__ __forceinline__ int risk_bin(double l3)
-{
-    const double x = (l3 + 8.0) * 16.0;
-    return !(x > 0.0) ? 0 : (x >= (double)(N_RISK_BINS - 1) ? N_RISK_BINS - 1 : (int)x);
-}
-
 template <bool EARLY>
 __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, double* pre, unsigned* bucket_count,
-                                                   unsigned char* bucket_of, unsigned char* risk_of, int64_t first,
-                                                   int64_t last)
+                                                   unsigned char* bucket_of, int64_t first, int64_t last)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
@@ -813,16 +668,12 @@ __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, 
         cvx::Arr<NT_P> M{smem + (size_t)100 * NT_P + tid};
         cvx::Arr<NT_P> T{smem + (size_t)155 * NT_P + tid};
         cvx::Arr<NT_P> L{smem + (size_t)211 * NT_P + tid};
-        const int rb = risk_bin(cvx::track_early(out, o, V, M, T, L));
-        risk_of[b] = (unsigned char)rb;
-        atomicAdd(bucket_count + 2 * N_BUCKETS + rb, 1u);   // risk histogram behind the bucket counts and offsets
+        cvx::track_early(out, o, V, M, T, L);
     }
 }
 
-// counting sort of the buckets -> queue order (likely stragglers first); risk histogram -> the bin from which a
-// problem also goes on the "risky first" list (about RISKY_FRAC of the batch: the largest third eigenvalues)
-constexpr double RISKY_FRAC = 0.03;
-__global__ void bucket_scan_kernel(const unsigned* count, unsigned* offset, unsigned long long* ctrl, int64_t batch)
+// counting sort of the buckets -> queue order (likely stragglers first)
+__global__ void bucket_scan_kernel(const unsigned* count, unsigned* offset)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned acc = 0;
@@ -830,34 +681,14 @@ __global__ void bucket_scan_kernel(const unsigned* count, unsigned* offset, unsi
             offset[k] = acc;
             acc += count[k];
         }
-        const unsigned* hist = count + 2 * N_BUCKETS;
-        unsigned top = 0;
-        int bin = N_RISK_BINS;   // no list unless the pre-pass filled the histogram
-        const unsigned want = (unsigned)(RISKY_FRAC * (double)batch);
-        for (int k = N_RISK_BINS - 1; k >= 1; --k) {
-            if (top + hist[k] > want + want / 2 && top > 0) break;   // a bin may overshoot the target by half, not more
-            top += hist[k];
-            if (hist[k]) bin = k;
-            if (top >= want) break;
-        }
-        ctrl[CTRL_RISK_BIN] = (unsigned long long)(top > 0 ? bin : N_RISK_BINS);
     }
 }
-__global__ void __launch_bounds__(256) bucket_scatter_kernel(int64_t batch, unsigned char* bucket_of,
-                                                             const unsigned char* risk_of, unsigned* offset, int32_t* order,
-                                                             unsigned long long* ctrl, int32_t* risky, unsigned risky_cap)
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(int64_t batch, const unsigned char* bucket_of,
+                                                             unsigned* offset, int32_t* order)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
-    const unsigned char k = bucket_of[b];
-    order[atomicAdd(offset + k, 1u)] = (int32_t)b;
-    if (risky && (unsigned long long)risk_of[b] >= ctrl[CTRL_RISK_BIN]) {
-        const unsigned long long r = atomicAdd(ctrl + CTRL_NRISKY, 1ULL);
-        if (r < risky_cap) {
-            risky[r] = (int32_t)b;
-            bucket_of[b] = k | 0x80;   // the main queue skips it
-        }
-    }
+    order[atomicAdd(offset + bucket_of[b], 1u)] = (int32_t)b;
 }
 
 // ---------------------------------------------------------------------------------
@@ -1261,9 +1092,8 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     return o;
 }
 
-// header: 16 control words, then the difficulty buckets of the work queue (64 counts, 64 offsets; unsigned int) and
-// the risk histogram (256 bins; unsigned int)
-constexpr int64_t WS_HEADER_DOUBLES = 16 + N_BUCKETS + N_RISK_BINS / 2;   // 16 x 8 B + 2 x 64 x 4 B + 256 x 4 B
+// header: 16 control words, then the difficulty buckets of the work queue (64 counts, 64 offsets; unsigned int)
+constexpr int64_t WS_HEADER_DOUBLES = 16 + N_BUCKETS;   // 16 x 8 B + 2 x 64 x 4 B
 
 // thread slots of the persistent grid: one CTA of NT threads per SM.  Without a
 // CUDA device (CPU-side callers sizing buffers) a generous 256 SMs is assumed.
@@ -1292,8 +1122,7 @@ int64_t device_slots(int64_t batch)
 //                    pre-pass 46 x batch doubles | hand-over slab 216 x slots doubles |
 //                    AA history AA_WORDS x slots words (stage kernel only; the fused kernel uses TMEM) |
 //                    FP32-phase export 166 x batch doubles | FP32 Q/rho 45 x 2 slots floats |
-//                    queue order batch x int32 | hand-back list batch x int32 | difficulty bucket batch x byte |
-//                    risk bin batch x byte]   (the "risky first" list of the tracked solver borrows the hand-over slab)
+//                    queue order batch x int32 | hand-back list batch x int32 | difficulty bucket batch x byte]
 size_t ws_bytes_for(int64_t slots, int64_t batch)
 {
     return (WS_HEADER_DOUBLES + (size_t)slots * 45 + (size_t)batch * (cvx::PARK_DOUBLES + cvx::PRE_DOUBLES) +
@@ -1302,8 +1131,8 @@ size_t ws_bytes_for(int64_t slots, int64_t batch)
            (size_t)slots * cvx::AA_WORDS * sizeof(float) +
            // FP32 first phase: exported state per problem, Q/rho scratch of its 2x wider grid
            (size_t)batch * cvx::WARM_DOUBLES * sizeof(double) + (size_t)slots * 2 * 45 * sizeof(float) +
-           // queue order (int32), list of problems handed back by the tracked solver (int32), bucket and risk bin (bytes)
-           (((size_t)batch * 10 + 15) / 16) * 16;
+           // queue order (int32), list of problems handed back by the tracked solver (int32) and bucket (byte) per problem
+           (((size_t)batch * 9 + 15) / 16) * 16;
 }
 
 }  // namespace
@@ -1397,10 +1226,6 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     int32_t* order = (int32_t*)(qr32 + slots * 2 * 45);
     int32_t* fail_list = order + d->batch;
     unsigned char* bucket_of = (unsigned char*)(fail_list + d->batch);
-    unsigned char* risk_of = bucket_of + d->batch;
-    int32_t* risky = (int32_t*)slab;   // free until the full-decomposition solver hands problems over
-    const unsigned long long risky_cap_ll = (unsigned long long)slots * cvx::HAND_DOUBLES * 2;
-    const unsigned risky_cap = risky_cap_ll > 0x7fffffffULL ? 0x7fffffffu : (unsigned)risky_cap_ll;
     unsigned* bucket_count = (unsigned*)(ctrl + 16);
     unsigned* bucket_offset = bucket_count + N_BUCKETS;
     mark(tm, 0, st);
@@ -1409,10 +1234,10 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         if (hi > lo) {
             if (early)
                 pre_kernel<true><<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_PE_BYTES, st>>>(
-                    dd, o, pre, bucket_count, bucket_of, risk_of, lo, hi);
+                    dd, o, pre, bucket_count, bucket_of, lo, hi);
             else
                 pre_kernel<false><<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(
-                    dd, o, pre, bucket_count, bucket_of, risk_of, lo, hi);
+                    dd, o, pre, bucket_count, bucket_of, lo, hi);
         }
         if (mode == 1) {
             g_launches = 1;
@@ -1421,9 +1246,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
             return 0;
         }
     }
-    bucket_scan_kernel<<<1, 32, 0, st>>>(bucket_count, bucket_offset, ctrl, d->batch);
-    bucket_scatter_kernel<<<(unsigned)((d->batch + 255) / 256), 256, 0, st>>>(d->batch, bucket_of, risk_of, bucket_offset, order,
-                                                                              ctrl, early ? risky : nullptr, risky_cap);
+    bucket_scan_kernel<<<1, 32, 0, st>>>(bucket_count, bucket_offset);
+    bucket_scatter_kernel<<<(unsigned)((d->batch + 255) / 256), 256, 0, st>>>(d->batch, bucket_of, bucket_offset, order);
     g_launches = (mode == 2) ? 4 : 5;   // pre-pass, two sort kernels, solver, finish
     const double* warm_in = nullptr;
     if (d->fp32_iters > 0) {
@@ -1450,23 +1274,15 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     if (tracked) {
         mark(tm, 7, st);
         // Stragglers of the tracked solver: one of its passes takes ~13 us, an iteration of the warp-per-problem kernel
-        // ~6.7 us, and the detour (cold decomposition, hand-over, resume) costs ~0.3 ms: it only pays for the last few
-        // problems of a batch, which keep the whole GPU waiting (measured, 1e5 PnPL 8+4: 1600 hand-overs at <= 2368
-        // alive cost 0.85 ms, 16 at <= 64 alive 0.1 ms of extra drain).
-        const int track_handoff_max = handoff_max < (int)(n_sm * N_SVC_WARPS) ? handoff_max : (int)(n_sm * N_SVC_WARPS);
-        const int track_grace = d->handoff != 0 ? grace : 8;
-        // the first svc_max hand-backs are served concurrently by the service warps (four per SM)
-        unsigned long long svc_max = (unsigned long long)n_sm * N_SVC_WARPS * 4;
-        if (const char* ev = getenv("CVX_SVC_MAX")) svc_max = (unsigned long long)atoll(ev);   // (experiments)
-        cudaMemsetAsync(fail_list, 0xFF, (size_t)d->batch * sizeof(int32_t), st);   // -1: entry not published yet
-        solve_track_kernel<<<(unsigned)blocks, NT_TRK, SMEM_TRK_BYTES, st>>>(dd, o, ctrl, pre, park, warm, warm_in, order, risky,
-                                                                             bucket_of, risky_cap, fail_list, track_grace,
-                                                                             track_handoff_max, svc_max);
+        // ~6.7 us, and the detour (cold decomposition, hand-over, resume) costs ~0.3 ms: handing over earlier than 64
+        // passes after the queue ran dry does not pay (1e5 PnPL 8+4: 1600 hand-overs at grace 40, 16 at 64).
+        const int track_grace = d->handoff != 0 ? grace : 64;
+        solve_track_kernel<<<(unsigned)blocks, NT, SMEM_TRK_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order, fail_list,
+                                                                         track_grace, handoff_max);
         mark(tm, 8, st);
         {
             const int64_t want_r = (d->batch + NT_R - 1) / NT_R, cap_r = n_sm * 4;   // grid-stride over the list
-            redecomp_kernel<<<(unsigned)(want_r < cap_r ? want_r : cap_r), NT_R, SMEM_R_BYTES, st>>>(ctrl, fail_list, pre, warm,
-                                                                                                 svc_max);
+            redecomp_kernel<<<(unsigned)(want_r < cap_r ? want_r : cap_r), NT_R, SMEM_R_BYTES, st>>>(ctrl, fail_list, pre, warm);
         }
         mark(tm, 3, st);
         solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm, fail_list,

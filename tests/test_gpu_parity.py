@@ -566,10 +566,11 @@ def test_fp32_admm_matches_oracle(cb, n_pts, n_lines):
 
 def test_kernel_times_and_launch_count(cb):
     """cvxpnpl_b200_kernel_times: CUDA-event time of every kernel of a timed solve; the
-    seven (nine) launches of the path are all there and add up to the step."""
+    nine (eleven with the FP32 first phase) launches of the tracked path are all there and add up to the step; the
+    full-decomposition path (psd="full") has seven."""
     from cvxpnpl_b200 import synth
     d = synth.make_batch(20000, 8, 4, noise=1.0, seed=5)
-    for admm, n_launch, extra in (("f64", 7, ()), ("f32", 9, ("admm32_kernel", "ortho_kernel"))):
+    for admm, n_launch, extra in (("f64", 9, ()), ("f32", 11, ("admm32_kernel", "ortho_kernel"))):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _solve(cb, d, 8, 4, admm_dtype=admm)        # warm-up
         s.record()
@@ -578,12 +579,44 @@ def test_kernel_times_and_launch_count(cb):
         torch.cuda.synchronize()
         assert res.launches == n_launch
         t = cb.last_kernel_times()
-        for k in ("pre_kernel", "solve_fused_kernel", "straggler_kernel", "solve_fused_kernel<resume>",
-                  "finish_kernel") + extra:
+        for k in ("pre_kernel", "solve_track_kernel", "redecomp_kernel", "solve_fused_kernel", "straggler_kernel",
+                  "solve_fused_kernel<resume>", "finish_kernel") + extra:
             assert t[k] > 0.0, (k, t)
         if admm == "f64":
             assert t["admm32_kernel"] == 0.0 and t["ortho_kernel"] == 0.0
         assert sum(t.values()) <= s.elapsed_time(e) * 1.05
+    full = _solve(cb, d, 8, 4, psd="full", timing=True)
+    assert full.launches == 7
+    t = cb.last_kernel_times()
+    assert t["solve_track_kernel"] == 0.0 and t["redecomp_kernel"] == 0.0 and t["solve_fused_kernel"] > 0.0
+
+
+@pytest.mark.parametrize("n_pts,n_lines,B", [(8, 4, 30000), (8, 0, 30000), (0, 6, 20000), (4, 0, 6000), (5, 3, 10000)])
+def test_tracked_psd_matches_full_decomposition(cb, n_pts, n_lines, B):
+    """The tracked-eigenpair PSD projection (pnpl_track.cuh: two eigenpairs refined per iteration + Cholesky
+    certificate; problems that fail it are finished with the full decomposition) against the full 10x10
+    decomposition every iteration (psd="full", the round-1 solver) on the same batch: same statuses, same number
+    of poses, same poses, about the same iteration counts."""
+    from cvxpnpl_b200 import synth
+    d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=1234)
+    a = _solve(cb, d, n_pts, n_lines, psd="full")
+    w = _solve(cb, d, n_pts, n_lines, psd="track")
+    assert w.launches == a.launches + 2          # solve_track_kernel + redecomp_kernel really ran
+    sa, sw = (a.status & 0xFF).cpu().numpy(), (w.status & 0xFF).cpu().numpy()
+    na, nw = a.n_poses.cpu().numpy(), w.n_poses.cpu().numpy()
+    well_posed = n_pts + n_lines >= 8
+    # a problem converges on both paths or on neither, up to the few that sit at the iteration cap
+    assert (sa != sw).mean() <= (1e-3 if well_posed else 5e-3)
+    ok = (sa == 0) & (sw == 0) & (na == 1) & (nw == 1)
+    assert ok.mean() > (0.98 if well_posed else 0.45)
+    assert ((na != nw) & (sa == 0) & (sw == 0)).mean() <= (1e-4 if well_posed else 5e-3)
+    Ra, Rw = a.R[:, 0].cpu().numpy()[ok], w.R[:, 0].cpu().numpy()[ok]
+    ta, tw = a.t[:, 0].cpu().numpy()[ok], w.t[:, 0].cpu().numpy()[ok]
+    ang = synth.rotation_angle(Ra, Rw)
+    terr = np.linalg.norm(ta - tw, axis=1) / np.linalg.norm(ta, axis=1)
+    assert ang.max() <= ROT_TOL and terr.max() <= T_TOL, (ang.max(), terr.max())
+    ia, iw = a.iters.cpu().numpy()[ok], w.iters.cpu().numpy()[ok]
+    assert abs(iw.mean() - ia.mean()) <= 0.03 * ia.mean() + 1
 
 
 def test_host_pipeline_matches_direct_solve(cb):
