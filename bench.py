@@ -281,8 +281,8 @@ class ClockSampler:
                 "reasons": sorted({x for r in inside for x in r[3]}), "samples": len(sm), "window": where}
 
 
-def _kernel_constants(n_pts, n_lines, B):
-    """ncu-counted constants of the dominant kernel (profiles/): the newest capture wins"""
+def _kernel_constants(n_pts, n_lines, B, kernel):
+    """ncu-counted constants of the dominant kernel (profiles/): the newest capture OF THAT KERNEL wins"""
     if (n_pts, n_lines, B) != (8, 4, 100_000):
         return {}
     for name in ("r2_kernel_constants.json", "r1_kernel_constants.json"):
@@ -290,6 +290,8 @@ def _kernel_constants(n_pts, n_lines, B):
         if os.path.exists(path):
             with open(path) as f:
                 kc = json.load(f)
+            if kc.get("kernel", "solve_fused_kernel").split("<")[0] not in kernel:
+                continue
             kc["source"] = "profiles/" + name
             return kc
     return {}
@@ -477,7 +479,7 @@ def run_ours(a):
     fp64_peak = cb.measure_fp64_peak(dev) if rank == 0 else None
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        kc = _kernel_constants(n_pts, n_lines, B)
+        kc = _kernel_constants(n_pts, n_lines, B, dominant)
         total = world * B * a.steps
         value = total / (ms_dev * 1e-3)
         e2e = total / (ms_e2e * 1e-3)

@@ -79,7 +79,8 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
     fp32_iters), the FP64 solver finishes to `eps`.
     psd: PSD projection of the ADMM iteration -- "track" (default): two tracked eigenpairs refined once per
     iteration with a certificate, problems that fail it are finished with the full decomposition; "full": a full
-    10x10 eigen-decomposition every iteration.
+    10x10 eigen-decomposition every iteration; "track1": the tracked projection with one thread per problem instead
+    of two (kept for A/B measurements).
     record: optional [B,15] float64 CUDA tensor (may be a slice of an all-gather buffer) that the finish
     kernel fills with the packed row (R0 | t0 | n_poses | status | iters) of every problem."""
     _require_cuda()
@@ -125,8 +126,8 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         raise ValueError("variant must be 'full' or 'rc'")
     if admm_dtype not in ("f64", "f32"):
         raise ValueError("admm_dtype must be 'f64' or 'f32'")
-    if psd not in ("track", "full"):
-        raise ValueError("psd must be 'track' or 'full'")
+    if psd not in ("track", "full", "track1"):
+        raise ValueError("psd must be 'track', 'full' or 'track1'")
     n_corr = (pts_2d.shape[1] if have_p else 0) + (line_2d.shape[1] if have_l else 0)
     if n_corr >= LARGE_N and B > 0:
         # many correspondences per problem (benchmarks/scalability/pnp.py:37-40): the
@@ -188,7 +189,7 @@ def solve_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, eps=1
         d.handoff = int(handoff)
         d.fp32_iters = int(fp32_iters) if admm_dtype == "f32" else 0
         d.timing = int(bool(timing))
-        d.psd_mode = {"track": 0, "full": 1}[psd]
+        d.psd_mode = {"track": 0, "full": 1, "track1": 2}[psd]
         d.R, d.t, d.n_poses, d.status, d.iters = _ptr(out.R), _ptr(out.t), _ptr(out.n_poses), _ptr(out.status), _ptr(out.iters)
         d.obj, d.Z = _ptr(out.obj), _ptr(out.Z)
         if record is not None:

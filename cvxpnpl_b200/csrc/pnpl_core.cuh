@@ -77,7 +77,9 @@ CVX_HD int sidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j 
 // Each off-diagonal entry of Z belongs to exactly one triple.  (i > j always.)
 // The last macro argument marks the three ROW-orthogonality triples, which (with the
 // three row-norm equalities) the "rc" ablation of benchmarks/toolkit/methods/rc.py drops.
-#define CVX_TRIPLES(X)                                        \
+// (two halves: the two-threads-per-problem form of the tracked solver gives the first eight to one thread, the last
+// seven and the diagonal equalities to the other)
+#define CVX_TRIPLES_A(X)                                      \
     X(1, 0, +1, 4, 3, +1, 7, 6, +1, 1)   /* r0.r1 */          \
     X(2, 0, +1, 5, 3, +1, 8, 6, +1, 1)   /* r0.r2 */          \
     X(2, 1, +1, 5, 4, +1, 8, 7, +1, 1)   /* r1.r2 */          \
@@ -85,7 +87,8 @@ CVX_HD int sidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j 
     X(6, 0, +1, 7, 1, +1, 8, 2, +1, 0)   /* c0.c2 */          \
     X(6, 3, +1, 7, 4, +1, 8, 5, +1, 0)   /* c1.c2 */          \
     X(5, 1, +1, 4, 2, -1, 9, 6, -1, 0)   /* (c0xc1)_0 = c2_0 */ \
-    X(3, 2, +1, 5, 0, -1, 9, 7, -1, 0)                        \
+    X(3, 2, +1, 5, 0, -1, 9, 7, -1, 0)
+#define CVX_TRIPLES_B(X)                                      \
     X(4, 0, +1, 3, 1, -1, 9, 8, -1, 0)                        \
     X(8, 4, +1, 7, 5, -1, 9, 0, -1, 0)   /* c1xc2 = c0 */     \
     X(6, 5, +1, 8, 3, -1, 9, 1, -1, 0)                        \
@@ -93,6 +96,7 @@ CVX_HD int sidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j 
     X(7, 2, +1, 8, 1, -1, 9, 3, -1, 0)   /* c2xc0 = c1 */     \
     X(8, 0, +1, 6, 2, -1, 9, 4, -1, 0)                        \
     X(6, 1, +1, 7, 0, -1, 9, 5, -1, 0)
+#define CVX_TRIPLES(X) CVX_TRIPLES_A(X) CVX_TRIPLES_B(X)
 
 // ---------------------------------------------------------------------------------
 // Assembly: correspondences -> Q (45 unique entries of the 9x9 block, packed lower)

@@ -231,9 +231,11 @@ struct ZRank2 {
     CVX_REAL a[10], ta[10], b[10], tb[10];   // Z = (t0 a) a' + (t1 b) b'
     CVX_HD CVX_REAL operator()(int i, int j) const { return fma(ta[i], a[j], tb[i] * b[j]); }
 };
-template <int S, class QR, class ZF>
-CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr, CVX_REAL alpha, CVX_REAL isig, CVX_REAL rowk,
-                                 const ZF& zf)
+// PART 2: everything; PART 0: the first eight triples; PART 1: the other seven and the diagonal equalities (the two
+// threads of a problem in the role-split solver, pnpl_track2.cuh; the return values add up).
+template <int PART, int S, class QR, class ZF>
+CVX_HD CVX_REAL dr_affine_part(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr, CVX_REAL alpha, CVX_REAL isig, CVX_REAL rowk,
+                               const ZF& zf)
 {
     CVX_REAL res = CVX_REAL(0.0);
     const CVX_REAL inrm9 = CVX_REAL(1.0) / (CVX_REAL(2.0) + isig * isig);
@@ -261,10 +263,15 @@ CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr
         G[e2] = alpha * d2;                                                                 \
         res += CVX_REAL(2.0) * (d0 * d0 + d1 * d1 + d2 * d2);                                         \
     }
-    CVX_TRIPLES(CVX_TRI)
+    if (PART != 1) {
+        CVX_TRIPLES_A(CVX_TRI)
+    }
+    if (PART != 0) {
+        CVX_TRIPLES_B(CVX_TRI)
+    }
 #undef CVX_TRI
     // diagonal block
-    {
+    if (PART != 0) {
         CVX_REAL w[9], md[10], zd[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) zd[i] = zf(i, i);
@@ -300,6 +307,13 @@ CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr
     }
 #undef CVX_Q
     return res;
+}
+
+template <int S, class QR, class ZF>
+CVX_HD CVX_REAL dr_affine_update(ArrT<S, CVX_REAL> M, ArrT<S, CVX_REAL> G, QR qr, CVX_REAL alpha, CVX_REAL isig, CVX_REAL rowk,
+                                 const ZF& zf)
+{
+    return dr_affine_part<2>(M, G, qr, alpha, isig, rowk, zf);
 }
 
 template <int S, class QR>

@@ -26,6 +26,7 @@
 #include "pnpl_solve.cuh"
 #include "pnpl_warp.cuh"
 #include "pnpl_track.cuh"
+#include "pnpl_track2.cuh"
 
 namespace {
 
@@ -111,6 +112,24 @@ __device__ __forceinline__ void HistTmem::ld<4>(int off, uint32_t* o) const
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : CVX_R4(o, 0) : "r"(base + (uint32_t)off) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::ld<2>(int off, uint32_t* o) const
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];"
+                 : "=r"(o[0]), "=r"(o[1]) : "r"(base + (uint32_t)off) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::st<2>(int off, const uint32_t* v) const
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};"
+                 : : "r"(base + (uint32_t)off), "r"(v[0]), "r"(v[1]) : "memory");
+}
+template <>
+__device__ __forceinline__ void HistTmem::st<16>(int off, const uint32_t* v) const
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 : : "r"(base + (uint32_t)off), CVX_V4(v, 0), CVX_V4(v, 4), CVX_V4(v, 8), CVX_V4(v, 12) : "memory");
 }
 template <>
 __device__ __forceinline__ void HistTmem::ld<8>(int off, uint32_t* o) const
@@ -232,6 +251,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
     // list modes: nothing handed over / handed back (the common case on well-posed batches) -> leave before the
     // tensor-memory allocation; a CTA beyond the list's length has nothing to do either
     if ((RESUME || from_track) && (unsigned long long)blockIdx.x * NT >= ctrl[RESUME ? CTRL_NSTRAG : CTRL_NFAIL]) return;
+    if (from_track > 1 && ctrl[CTRL_NFAIL] <= (unsigned long long)(from_track - 1)) return;   // (from_track = 1 + direct_max)
 
     cvx::Arr<NT> V{smem + tid};
     cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
@@ -453,15 +473,183 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
     tmem_free_all(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------
+// Tracked persistent solver, TWO threads per problem (pnpl_track2.cuh): 256 threads per CTA, still 128 problems per
+// SM; thread p of warps 0-3 (role A) and thread p of warps 4-7 (role B) own problem slot p together.  Warp w and
+// warp w + 4 address the same tensor-memory lanes (role A uses columns 0-255, role B 256-511 of each lane); all eight
+// warps meet at a CTA barrier between the phases of a pass (the barrier a pair needs, widened to the CTA so that the
+// four warps of a role stay in lock-step and share the instruction-cache lines of the role's code).  Role A owns the queue, the hand-over
+// decision, parking and hand-back; role B follows through a control word in shared memory.
+// Shared memory per problem: the 178 doubles of solve_track_kernel + 5 doubles and 22 floats of exchange scratch.
+// ---------------------------------------------------------------------------------
+constexpr int NT2 = 2 * NT;
+constexpr int TRK2_X = TRK_SMEM_DOUBLES;                          // exchange doubles
+constexpr int TRK2_XF = TRK_SMEM_DOUBLES + cvx::X2_DOUBLES;       // exchange floats (22 floats = 11 doubles)
+constexpr int TRK2_SMEM_DOUBLES = TRK2_XF + cvx::X2_FLOATS / 2;
+constexpr size_t SMEM_TRK2_BYTES = (size_t)NT * TRK2_SMEM_DOUBLES * sizeof(double);
+
+// CTA-wide barrier / votes from the two role-specific code paths: named barrier 1 with an explicit thread count (the
+// hardware counts arrivals, whatever instruction they come from)
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { asm volatile("barrier.cta.sync 1, %0;" ::"n"(2 * NT) : "memory"); }
+};
+struct CtaVote {
+    __device__ __forceinline__ bool operator()(bool f) const
+    {
+        uint32_t r;
+        asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; barrier.cta.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(r) : "r"((uint32_t)f), "n"(2 * NT) : "memory");
+        return r != 0;
+    }
+};
+__device__ __forceinline__ bool cta_vote_and(bool f)
+{
+    uint32_t r;
+    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; barrier.cta.red.and.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "r"((uint32_t)f), "n"(2 * NT) : "memory");
+    return r != 0;
+}
+
+// (one function for both roles, the role a run-time value: everything the two threads of a problem do alike -- most of a
+// pass -- is then the SAME instructions for all eight warps, which walk them in lock-step out of one instruction stream)
+__device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_desc& d, const Opts& o, unsigned long long* ctrl,
+                                            double* pre, double* park, const double* warm, const int32_t* order,
+                                            int32_t* fail_list, int grace, int handoff_max, double* smem, uint32_t tmem_base,
+                                            int* queue_dry)
+{
+    const int p = threadIdx.x & (NT - 1);
+    const int wq = (threadIdx.x >> 5) & 3;
+    cvx::Arr<NT> M{smem + p};
+    cvx::Arr<NT> G{smem + (size_t)55 * NT + p};
+    cvx::Arr<NT> U{smem + (size_t)111 * NT + p};
+    cvx::Arr<NT> TH{smem + (size_t)131 * NT + p};
+    cvx::Arr<NT> QR{smem + (size_t)133 * NT + p};
+    cvx::Arr<NT> X{smem + (size_t)TRK2_X * NT + p};
+    cvx::ArrT<NT, float> XF{reinterpret_cast<float*>(smem + (size_t)TRK2_XF * NT) + p};
+    const HistTmem H{tmem_base + ((uint32_t)wq << 21)};
+    const CtaSync sync;
+    const CtaVote vote;
+    {
+        uint32_t zero[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) zero[u] = 0u;
+        for (int c = 0; c < cvx::A2_ROLE_WORDS / 32; ++c) H.st<32>(ROLE * cvx::A2_ROLE_WORDS + 32 * c, zero);
+        H.wait_st();
+    }
+    if (ROLE == 0) G[55] = 0.0;
+    int64_t b = -1;
+    bool exhausted = false, counted = false;
+    int drain = 0;
+    const unsigned long long n_work = (unsigned long long)d.batch;
+    cvx::LaneState st;
+    st.finite = false;
+    st.iterating = false;
+    st.converged = false;
+    st.it = 0;
+    st.phase = 0;
+    st.bad = 0;
+    st.rho = 0.0;
+    st.dobj = 0.0;
+    st.res_prev = 1e300;
+    cvx::aa_reset(st.aa);
+    int wslot = 0;
+    // (Tried and dropped, profiles/README.md r2p: copying the next record in with 8-byte cp.async while the lane pair
+    // sits out one pass -- 3.86 -> 4.12 ms: the idle pass and 125 LDGSTS per record cost more than the load latency
+    // they take off the path.)
+    for (;;) {
+        bool fresh = false;
+        if (ROLE == 0) {
+            double ctl = -1.0;
+            if (b < 0) {
+                if (!exhausted) {
+                    const unsigned long long nb = atomicAdd(ctrl + CTRL_TRK_NEXT, 1ULL);
+                    if (nb < n_work) {
+                        b = (int64_t)order[nb];
+                        ctl = (double)b;
+                        fresh = true;
+                    } else {
+                        exhausted = true;
+                        *queue_dry = 1;
+                    }
+                }
+            } else if (grace >= 0 && st.iterating) {
+                if (drain > 0 || *(volatile int*)queue_dry) {
+                    if (!counted) {
+                        atomicAdd(ctrl + CTRL_ACTIVE, 1ULL);
+                        counted = true;
+                    }
+                    ++drain;
+                }
+                if (drain > grace && *(volatile unsigned long long*)(ctrl + CTRL_ACTIVE) <= (unsigned long long)handoff_max)
+                    ctl = -3.0;
+            }
+            X[cvx::X2_CTL] = ctl;
+        }
+        if (cta_vote_and(b < 0)) break;
+        const double ctl = X[cvx::X2_CTL];
+        if (ROLE == 1 && b < 0 && ctl >= 0.0) {
+            b = (int64_t)ctl;
+            fresh = true;
+        }
+        const bool give_up = b >= 0 && ctl == -3.0;
+        if (fresh) {
+            const double* rec = pre + b * cvx::PRE_DOUBLES;
+            if (warm) {
+                if (ROLE == 0) cvx::t2_begin_warm<0>(rec, warm + b * cvx::WARM_DOUBLES, o, M, U, TH, QR, st);
+                else cvx::t2_begin_warm<1>(rec, warm + b * cvx::WARM_DOUBLES, o, M, U, TH, QR, st);
+            } else {
+                if (ROLE == 0) cvx::t2_begin<0>(rec, o, M, U, TH, QR, st);
+                else cvx::t2_begin<1>(rec, o, M, U, TH, QR, st);
+            }
+        }
+        sync();
+        int rc = cvx::t2_pass(ROLE, o, b >= 0 && !give_up, M, G, U, TH, QR, X, XF, H, st, wslot, sync, vote);
+        wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
+        if (b >= 0) {
+            if (give_up) rc = -1;
+            if (rc > 0) {
+                if (ROLE == 0) cvx::track_park(o, U, TH, st, park + b * cvx::PARK_DOUBLES, d.iters + b);
+                b = -1;
+            } else if (rc < 0) {
+                if (ROLE == 0) {
+                    cvx::track_handoff(M, QR, st, pre + b * cvx::PRE_DOUBLES);
+                    fail_list[atomicAdd(ctrl + CTRL_NFAIL, 1ULL)] = (int32_t)b;
+                    if (give_up) exhausted = true;
+                }
+                b = -1;
+            }
+            if (ROLE == 0 && counted && (b < 0 || !st.iterating)) {
+                atomicAdd(ctrl + CTRL_ACTIVE, ~0ULL);
+                counted = false;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT2, 1)
+solve_track2_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double* pre, double* park, const double* warm,
+                    const int32_t* order, int32_t* fail_list, int grace, int handoff_max)
+{
+    extern __shared__ double smem[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int queue_dry;
+    if (threadIdx.x == 0) queue_dry = 0;
+    const uint32_t tmem_base = tmem_alloc_all(&tmem_slot);
+    track2_loop(threadIdx.x < NT ? 0 : 1, d, o, ctrl, pre, park, warm, order, fail_list, grace, handoff_max, smem, tmem_base,
+                &queue_dry);
+    tmem_free_all(tmem_base);
+}
+
 // Problems handed back by the tracked solver: cold eigen-decomposition of their DR iterate M (cyclic Jacobi,
 // lane-parallel), exported in the WARM format the full-decomposition solver starts from.
 constexpr int NT_R = 64;
 constexpr size_t SMEM_R_BYTES = (size_t)NT_R * 100 * sizeof(double);
 __global__ void __launch_bounds__(NT_R) redecomp_kernel(const unsigned long long* ctrl, const int32_t* fail_list,
-                                                        const double* pre, double* warm)
+                                                        const double* pre, double* warm, int direct_max)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
+    if (ctrl[CTRL_NFAIL] <= (unsigned long long)direct_max) return;   // few: straight to the warp-per-problem kernel
     for (unsigned long long k = (unsigned long long)blockIdx.x * NT_R + tid; k < ctrl[CTRL_NFAIL];
          k += (unsigned long long)gridDim.x * NT_R) {
     const int64_t b = fail_list[k];
@@ -564,26 +752,57 @@ __global__ void __launch_bounds__(128) ortho_kernel(int64_t batch, double* warm)
 // ---------------------------------------------------------------------------------
 constexpr int NT_W = 256;
 constexpr size_t SMEM_W_BYTES = (NT_W / 32) * sizeof(cvx::WarpSmem);
-__global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned long long* ctrl, double* slab)
+// DIRECT mode (fail_list != nullptr and the tracked solver handed back no more problems than there are warps here,
+// `direct_max`): the entries are taken straight from the tracked solver's hand-back list -- iterate M, Q/rho, rho and
+// the iteration count from the problem's record, eigen-decomposition by a warp-cooperative cold Jacobi -- instead of
+// going through redecomp_kernel and one pass of the thread solver first (~0.17 ms of latency for a handful of problems).
+__global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned long long* ctrl, double* slab,
+                                                            const int32_t* fail_list, const double* pre, int direct_max)
 {
     extern __shared__ double smem[];
     cvx::WarpSmem& S = reinterpret_cast<cvx::WarpSmem*>(smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const unsigned long long n = ctrl[CTRL_NSTRAG];
+    const unsigned long long n_fail = fail_list ? ctrl[CTRL_NFAIL] : 0ULL;
+    const bool direct = n_fail > 0 && n_fail <= (unsigned long long)direct_max;
+    const unsigned long long n = direct ? n_fail : ctrl[CTRL_NSTRAG];
+    uint32_t pk[9];
+    cvx::sweep_tables(lane, pk);
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(ctrl + CTRL_STRAG_NEXT, 1ULL);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n) break;
         double* h = slab + k * cvx::HAND_DOUBLES;
-        // slab entry -> full-form matrices in shared memory
-        for (int e = lane; e < 100; e += 32) {
-            const int r = e / 10, c = e - 10 * r;
-            S.M[e] = h[cvx::HO_M + cvx::sidx(r, c)];
-            S.V[e] = h[cvx::HO_V + e];
-            S.Q[e] = (r < 9 && c < 9) ? h[cvx::HO_Q + cvx::sidx(r, c)] : 0.0;
+        bool dr_over = false, conv_in = false;
+        if (direct) {
+            const int64_t b = fail_list[k];
+            const double* rec = pre + b * cvx::PRE_DOUBLES;
+            for (int e = lane; e < 100; e += 32) {
+                const int r = e / 10, c = e - 10 * r;
+                S.M[e] = rec[cvx::TR_M + cvx::sidx(r, c)];
+                S.Q[e] = (r < 9 && c < 9) ? rec[cvx::TR_Q + cvx::sidx(r, c)] : 0.0;
+            }
+            const int fl = (int)rec[cvx::TR_FLAGS];
+            dr_over = (fl & 1) != 0;
+            conv_in = (fl & 2) != 0;
+            if (lane == 0) {
+                h[cvx::HO_IT] = rec[cvx::TR_IT];
+                h[cvx::HO_RHO] = rec[cvx::TR_RHO];
+                h[cvx::HO_B] = (double)b;
+                if (k == 0) ctrl[CTRL_NSTRAG] = n_fail;   // what the resume kernel (next launch) works through
+            }
+            __syncwarp();
+            cvx::warp_cold_decompose(S, lane, pk);
+        } else {
+            // slab entry -> full-form matrices in shared memory
+            for (int e = lane; e < 100; e += 32) {
+                const int r = e / 10, c = e - 10 * r;
+                S.M[e] = h[cvx::HO_M + cvx::sidx(r, c)];
+                S.V[e] = h[cvx::HO_V + e];
+                S.Q[e] = (r < 9 && c < 9) ? h[cvx::HO_Q + cvx::sidx(r, c)] : 0.0;
+            }
+            if (lane < 10) S.L[lane] = h[cvx::HO_L + lane];
         }
-        if (lane < 10) S.L[lane] = h[cvx::HO_L + lane];
         for (int e = lane; e < 56; e += 32) {
             S.gp[e] = S.sp[e] = S.gk[e] = 0.f;
 #pragma unroll
@@ -594,8 +813,8 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
         int it = (int)h[cvx::HO_IT];
         double rho = h[cvx::HO_RHO];
         __syncwarp();
-        bool converged = false;
-        cvx::warp_dr_loop(S, o, lane, it, converged, rho, o.max_iters);
+        bool converged = conv_in;
+        if (!dr_over) cvx::warp_dr_loop(S, o, lane, it, converged, rho, o.max_iters);
         for (int p = lane; p < 55; p += 32) {
             int r, c;
             cvx::unpack_idx(p, r, c);
@@ -1181,6 +1400,9 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
                 e = cudaFuncSetAttribute(solve_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_TRK_BYTES);
             if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(solve_track2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_TRK2_BYTES);
+            if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(redecomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_R_BYTES);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(admm32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM32_BYTES);
@@ -1216,7 +1438,7 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     }
     // PSD projection: tracked eigenpairs (default) or the full decomposition every iteration (desc.psd_mode = 1;
     // also for batches that fit the warp-per-problem grid, which go there at once)
-    const bool tracked = d->psd_mode == 0 && d->batch > n_sm * 2 * (NT_W / 32);
+    const bool tracked = d->psd_mode != 1 && d->batch > n_sm * 2 * (NT_W / 32);
     const bool early = tracked && d->fp32_iters <= 0;   // the FP32 first phase starts from the start decomposition
     const bool tm = d->timing != 0 && mode != 1;
     g_ev_n = 0;
@@ -1271,22 +1493,29 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     if (wblocks > wcap) wblocks = wcap;
     // (two or three problems per warp were measured too: no difference)
     const int handoff_max = (int)(wblocks * warps_per_cta);
+    // a hand-back list no longer than the warp-per-problem grid goes straight there (straggler_kernel, DIRECT mode)
+    const int direct_max = (tracked && grace >= 0) ? handoff_max : 0;
     if (tracked) {
         mark(tm, 7, st);
         // Stragglers of the tracked solver: one of its passes takes ~13 us, an iteration of the warp-per-problem kernel
         // ~6.7 us, and the detour (cold decomposition, hand-over, resume) costs ~0.3 ms: handing over earlier than 64
         // passes after the queue ran dry does not pay (1e5 PnPL 8+4: 1600 hand-overs at grace 40, 16 at 64).
         const int track_grace = d->handoff != 0 ? grace : 64;
-        solve_track_kernel<<<(unsigned)blocks, NT, SMEM_TRK_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order, fail_list,
-                                                                         track_grace, handoff_max);
+        if (d->psd_mode == 2)   // one thread per problem (the round-2a form, kept for A/B runs)
+            solve_track_kernel<<<(unsigned)blocks, NT, SMEM_TRK_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order,
+                                                                             fail_list, track_grace, handoff_max);
+        else
+            solve_track2_kernel<<<(unsigned)blocks, NT2, SMEM_TRK2_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order,
+                                                                                fail_list, track_grace, handoff_max);
         mark(tm, 8, st);
         {
             const int64_t want_r = (d->batch + NT_R - 1) / NT_R, cap_r = n_sm * 4;   // grid-stride over the list
-            redecomp_kernel<<<(unsigned)(want_r < cap_r ? want_r : cap_r), NT_R, SMEM_R_BYTES, st>>>(ctrl, fail_list, pre, warm);
+            redecomp_kernel<<<(unsigned)(want_r < cap_r ? want_r : cap_r), NT_R, SMEM_R_BYTES, st>>>(ctrl, fail_list, pre, warm,
+                                                                                                 direct_max);
         }
         mark(tm, 3, st);
         solve_fused_kernel<false><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, warm, fail_list,
-                                                                            grace, handoff_max, slots, 1);
+                                                                            grace, handoff_max, slots, 1 + direct_max);
         g_launches += 2;
     } else {
         mark(tm, 3, st);
@@ -1295,7 +1524,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     }
     if (grace >= 0) {
         mark(tm, 4, st);
-        straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab);
+        straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab, tracked ? fail_list : nullptr, pre,
+                                                                        direct_max);
         mark(tm, 5, st);
         solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, nullptr,
                                                                           -1, 0, slots, 0);

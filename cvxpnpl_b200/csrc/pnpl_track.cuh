@@ -500,26 +500,15 @@ CVX_HD void track_begin_warm(const double* rec, const double* w, const Opts& o, 
     if (st.finite && !st.iterating) st.phase = 1;
 }
 
-// Part 1 of a pass: one DR iteration from the tracked pairs (same rules as pass_dr).
+// What follows a DR iteration with squared residual `res` (same rules as pass_dr): end of the DR loop, plateau jump
+// (applied to the entries [e_lo, e_hi) of M: all of them, or one thread's share in the role-split solver), Anderson
+// bookkeeping.  Returns true when the problem wants an Anderson step on the iterate it just produced.
 template <int S>
-CVX_HD bool track_pass_dr(const Opts& o, Arr<S> M, Arr<S> G, Arr<S> U, Arr<S> TH, Arr<S> QR, LaneState& st)
+CVX_HD bool track_decide(const Opts& o, LaneState& st, double res, Arr<S> M, Arr<S> G, int e_lo, int e_hi)
 {
-    if (!st.finite || !st.iterating) return false;
-    ZRank2 zf;
-    {
-        const double t0 = fmax(TH[0], 0.0), t1 = fmax(TH[1], 0.0);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            zf.a[i] = U[i];
-            zf.b[i] = U[10 + i];
-            zf.ta[i] = t0 * zf.a[i];
-            zf.tb[i] = t1 * zf.b[i];
-        }
-    }
-    const double res = dr_affine_update(M, G, QR, o.alpha, 1.0 / o.sigma, o.rowk, zf);
     ++st.it;
 #if defined(CVX_TRACE) && !defined(__CUDA_ARCH__)
-    printf("trk it %d res %.3e aa_mask %u th %.4e %.4e\n", st.it, sqrt(res), st.aa.mask, (double)TH[0], (double)TH[1]);
+    printf("trk it %d res %.3e aa_mask %u\n", st.it, sqrt(res), st.aa.mask);
 #endif
     if (!(res > o.eps2) && (st.bad == 0 || !(res <= o.eps2))) {  // also leaves on NaN; never converges on an uncertified projection
         st.converged = (res <= o.eps2);
@@ -543,7 +532,7 @@ CVX_HD bool track_pass_dr(const Opts& o, Arr<S> M, Arr<S> G, Arr<S> U, Arr<S> TH
         if (tau > 0) {
             const double ft = (double)tau;
 #pragma unroll 1
-            for (int e = 0; e < 55; ++e) M[e] = fma(ft, G[e], M[e]);
+            for (int e = e_lo; e < e_hi; ++e) M[e] = fma(ft, G[e], M[e]);
             aa_reset(st.aa);
             st.res_prev = res;
             return false;
@@ -553,6 +542,26 @@ CVX_HD bool track_pass_dr(const Opts& o, Arr<S> M, Arr<S> G, Arr<S> U, Arr<S> TH
     if (!tail || res > 4.0 * st.res_prev) aa_reset(st.aa);
     st.res_prev = res;
     return tail;
+}
+
+// Part 1 of a pass: one DR iteration from the tracked pairs (same rules as pass_dr).
+template <int S>
+CVX_HD bool track_pass_dr(const Opts& o, Arr<S> M, Arr<S> G, Arr<S> U, Arr<S> TH, Arr<S> QR, LaneState& st)
+{
+    if (!st.finite || !st.iterating) return false;
+    ZRank2 zf;
+    {
+        const double t0 = fmax(TH[0], 0.0), t1 = fmax(TH[1], 0.0);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            zf.a[i] = U[i];
+            zf.b[i] = U[10 + i];
+            zf.ta[i] = t0 * zf.a[i];
+            zf.tb[i] = t1 * zf.b[i];
+        }
+    }
+    const double res = dr_affine_update(M, G, QR, o.alpha, 1.0 / o.sigma, o.rowk, zf);
+    return track_decide(o, st, res, M, G, 0, 55);
 }
 
 // Part 2 of a pass: refine the tracked pairs for the new M; penalty rescale; end of the DR loop.

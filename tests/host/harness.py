@@ -22,10 +22,10 @@ def load():
     global _lib
     if _lib is None:
         srcs = [os.path.join(_HERE, "host_harness.cpp")] + [
-            os.path.join(_ROOT, "cvxpnpl_b200", "csrc", f) for f in ("pnpl_core.cuh", "pnpl_dr.inl", "pnpl_extract.cuh", "pnpl_solve.cuh", "pnpl_track.cuh")]
+            os.path.join(_ROOT, "cvxpnpl_b200", "csrc", f) for f in ("pnpl_core.cuh", "pnpl_dr.inl", "pnpl_extract.cuh", "pnpl_solve.cuh", "pnpl_track.cuh", "pnpl_track2.cuh")]
         if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
             os.makedirs(os.path.dirname(_SO), exist_ok=True)
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _SO, srcs[0]])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", _SO, srcs[0]])
         _lib = ctypes.CDLL(_SO)
     return _lib
 
@@ -44,16 +44,17 @@ def solve(d, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0
     return dict(R=R, t=t, n_poses=n, status=st, iters=it, obj=obj, Z=Z)
 
 
-def solve_track(d, eps=1e-9, max_iters=2500, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=1, variant=0):
+def solve_track(d, eps=1e-9, max_iters=2500, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=1, variant=0, two=False):
     """The tracked solver (pnpl_track.cuh) chained like the CUDA kernels chain it; r["fallbacks"][b] = 1 where
-    the certificate failed and the full-decomposition path finished the problem."""
+    the certificate failed and the full-decomposition path finished the problem.  two=True: the role-split form
+    (pnpl_track2.cuh), two host threads per problem with a barrier where the kernel has its named barriers."""
     lib = load()
     B, n_pts, n_lines = d["pts_2d"].shape[0], d["pts_2d"].shape[1], d["line_2d"].shape[1]
     c = {k: np.ascontiguousarray(d[k], dtype=np.float64) for k in ("K", "pts_2d", "pts_3d", "line_2d", "line_3d")}
     R, t = np.empty((B, 4, 3, 3)), np.empty((B, 4, 3))
     n, st, it, fb = (np.empty(B, np.int32) for _ in range(4))
     obj, Z = np.empty((B, 2)), np.empty((B, 10, 10))
-    lib.host_solve_track(ctypes.c_int64(B), n_pts, n_lines, _p(c["K"]), int(c["K"].ndim == 3), _p(c["pts_2d"]),
+    (lib.host_solve_track2 if two else lib.host_solve_track)(ctypes.c_int64(B), n_pts, n_lines, _p(c["K"]), int(c["K"].ndim == 3), _p(c["pts_2d"]),
                          _p(c["pts_3d"]), _p(c["line_2d"]), _p(c["line_3d"]), ctypes.c_double(eps), max_iters,
                          ctypes.c_double(rho_rel), ctypes.c_double(alpha), ctypes.c_double(sigma), int(anderson),
                          int(variant), _p(R), _p(t), n.ctypes.data_as(_ip), st.ctypes.data_as(_ip),

@@ -234,3 +234,162 @@ extern "C" int host_solve_track(int64_t B, int n_pts, int n_lines, const double*
     }
     return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------
+// The role-split tracked solver (pnpl_track2.cuh) with two host threads standing in for the two CUDA threads of a
+// problem, and a spinning barrier where the kernel has its named barrier.
+// ---------------------------------------------------------------------------------------
+#include <atomic>
+#include <thread>
+#include "../../cvxpnpl_b200/csrc/pnpl_track2.cuh"
+
+namespace {
+struct SpinBarrier {
+    std::atomic<int> count{0};
+    std::atomic<int> sense{0};
+    void wait()
+    {
+        const int s = sense.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) == 1) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(1 - s, std::memory_order_release);
+        } else {
+            while (sense.load(std::memory_order_acquire) == s) std::this_thread::yield();
+        }
+    }
+};
+struct PairSync {
+    SpinBarrier* b;
+    void operator()() const { b->wait(); }
+};
+struct PairVote {   // both threads hold the same value: the vote is the value (plus the barrier the kernel's vote implies)
+    SpinBarrier* b;
+    bool operator()(bool f) const { b->wait(); return f; }
+};
+struct Shared2 {
+    std::vector<double> V, M, T, L, qr, U, TH, X, Qs, Bs;
+    std::vector<float> XF;
+    std::vector<uint32_t> hist;
+    double rec[cvx::PRE_DOUBLES], park[cvx::PARK_DOUBLES];
+    Shared2() : V(100), M(56), T(56), L(10), qr(45), U(20), TH(2), X(cvx::X2_DOUBLES), Qs(45), Bs(27), XF(cvx::X2_FLOATS), hist(cvx::AA_WORDS, 0u) {}
+};
+struct Args2 {
+    int64_t B; int n_pts, n_lines; const double* K; int k_batched; const double *pts_2d, *pts_3d, *line_2d, *line_3d;
+    cvx::Opts o; double *R, *t; int32_t *n_poses, *status, *iters; double *obj, *Z; int32_t* fallbacks;
+};
+
+template <int ROLE>
+void role_thread(const Args2& a, Shared2& sh, SpinBarrier& bar)
+{
+    const cvx::Opts& o = a.o;
+    cvx::Arr<1> aV{sh.V.data()}, aM{sh.M.data()}, aT{sh.T.data()}, aL{sh.L.data()}, aQ{sh.qr.data()}, aU{sh.U.data()},
+        aTH{sh.TH.data()}, aX{sh.X.data()};
+    cvx::ArrT<1, float> aXF{sh.XF.data()};
+    const cvx::HistMem H{sh.hist.data(), 1};
+    const PairSync sync{&bar};
+    const PairVote vote{&bar};
+    for (int64_t b = 0; b < a.B; ++b) {
+        cvx::Problem pr;
+        pr.K = a.k_batched ? a.K + 9 * b : a.K;
+        pr.pts_2d = a.pts_2d + b * 2 * a.n_pts;
+        pr.pts_3d = a.pts_3d + b * 3 * a.n_pts;
+        pr.line_2d = a.line_2d + b * 4 * a.n_lines;
+        pr.line_3d = a.line_3d + b * 6 * a.n_lines;
+        pr.n_pts = a.n_pts;
+        pr.n_lines = a.n_lines;
+        if (ROLE == 0) {
+            cvx::assemble_scaled(pr, o, sh.rec);
+            cvx::start_decomposition(sh.rec, o, aV);
+            cvx::track_early(sh.rec, o, aV, aM, aT, aL);
+            sh.T[55] = 0.0;
+        }
+        bar.wait();
+        cvx::LaneState st;
+        cvx::t2_begin<ROLE>(sh.rec, o, aM, aU, aTH, aQ, st);
+        bar.wait();
+        int wslot = 0, rc = 0;
+        for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+            rc = cvx::t2_pass(ROLE, o, true, aM, aT, aU, aTH, aQ, aX, aXF, H, st, wslot, sync, vote);
+            wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
+            bar.wait();
+            if (rc != 0) break;
+        }
+        if (ROLE == 0) {
+            int32_t it_out = 0;
+            const bool handed = rc < 0;
+            cvx::Result rs;
+            if (handed) {
+                cvx::track_handoff(aM, aQ, st, sh.rec);
+                for (int e = 0; e < 55; ++e) sh.T[e] = sh.M[e];
+                for (int i = 0; i < 10; ++i)
+                    for (int j = 0; j < 10; ++j) sh.V[i * 10 + j] = (i == j);
+                for (int s = 0; s < 12; ++s) {
+                    double dg = 0;
+                    for (int j = 0; j < 10; ++j) dg += sh.T[cvx::sidx(j, j)] * sh.T[cvx::sidx(j, j)];
+                    if (!(cvx::jacobi_sweep(aT, aV) > 1e-26 * dg)) break;
+                }
+                for (int j = 0; j < 10; ++j) sh.L[j] = sh.T[cvx::sidx(j, j)];
+                sh.T[55] = 0.0;
+                std::fill(sh.hist.begin(), sh.hist.end(), 0u);
+                cvx::aa_reset(st.aa);
+                st.res_prev = 1e300;
+                st.phase = st.iterating ? 0 : 1;
+                int ws2 = 0;
+                for (int guard = 0; guard < o.max_iters + 40; ++guard) {
+                    const bool want = cvx::pass_dr(o, aV, aM, aT, aL, aQ, st);
+                    if (want) cvx::aa_step(aM, aT, H, st.aa, want, ws2, (float)st.res_prev);
+                    ws2 = (ws2 + 1 == cvx::AA_M) ? 0 : ws2 + 1;
+                    if (cvx::pass_eig(o, aV, aM, aT, aL, aQ, st)) break;
+                }
+                cvx::problem_park(aV, aL, st, sh.park, &it_out);
+                std::fill(sh.hist.begin(), sh.hist.end(), 0u);
+            } else {
+                cvx::track_park(o, aU, aTH, st, sh.park, &it_out);
+            }
+            cvx::extract_parked(pr, o, sh.park, aV, cvx::Arr<1>{sh.Qs.data()}, cvx::Arr<1>{sh.Bs.data()}, a.R + b * 36,
+                                a.t + b * 12, a.Z ? a.Z + b * 100 : nullptr, rs);
+            a.n_poses[b] = rs.n_poses;
+            a.status[b] = rs.status;
+            a.iters[b] = it_out;
+            if (a.fallbacks) a.fallbacks[b] = handed ? 1 : 0;
+            if (a.obj) {
+                a.obj[2 * b] = rs.pobj;
+                a.obj[2 * b + 1] = rs.dobj;
+            }
+        }
+        bar.wait();
+    }
+}
+}  // namespace
+
+extern "C" int host_solve_track2(int64_t B, int n_pts, int n_lines, const double* K, int k_batched,
+                                 const double* pts_2d, const double* pts_3d, const double* line_2d,
+                                 const double* line_3d, double eps, int max_iters, double rho_rel, double alpha,
+                                 double sigma, int anderson, int variant, double* R, double* t, int32_t* n_poses,
+                                 int32_t* status, int32_t* iters, double* obj, double* Z, int32_t* fallbacks)
+{
+    Args2 a;
+    a.B = B; a.n_pts = n_pts; a.n_lines = n_lines; a.K = K; a.k_batched = k_batched;
+    a.pts_2d = pts_2d; a.pts_3d = pts_3d; a.line_2d = line_2d; a.line_3d = line_3d;
+    a.R = R; a.t = t; a.n_poses = n_poses; a.status = status; a.iters = iters; a.obj = obj; a.Z = Z; a.fallbacks = fallbacks;
+    cvx::Opts& o = a.o;
+    o.eps2 = eps * eps;
+    o.alpha = alpha;
+    o.rho_rel = rho_rel;
+    o.max_iters = max_iters > 0 ? max_iters : 2500;
+    o.sweeps = 1;
+    o.sigma = sigma;
+    cvx::default_params(n_pts, o.rho_rel, o.alpha, o.sigma);
+    o.anderson = anderson != 0;
+    o.rowk = variant == 1 ? 0.0 : 1.0;
+    o.kappa = cvx::DUAL_GUESS;
+    o.aa_on2 = cvx::AA_RES2_ON;
+    o.early = cvx::default_early(n_pts, n_lines);
+    Shared2 sh;
+    SpinBarrier bar;
+    std::thread t1([&] { role_thread<1>(a, sh, bar); });
+    role_thread<0>(a, sh, bar);
+    t1.join();
+    return 0;
+}

@@ -591,16 +591,18 @@ def test_kernel_times_and_launch_count(cb):
     assert t["solve_track_kernel"] == 0.0 and t["redecomp_kernel"] == 0.0 and t["solve_fused_kernel"] > 0.0
 
 
+@pytest.mark.parametrize("psd", ["track", "track1"])
 @pytest.mark.parametrize("n_pts,n_lines,B", [(8, 4, 30000), (8, 0, 30000), (0, 6, 20000), (4, 0, 6000), (5, 3, 10000)])
-def test_tracked_psd_matches_full_decomposition(cb, n_pts, n_lines, B):
+def test_tracked_psd_matches_full_decomposition(cb, n_pts, n_lines, B, psd):
     """The tracked-eigenpair PSD projection (pnpl_track.cuh: two eigenpairs refined per iteration + Cholesky
     certificate; problems that fail it are finished with the full decomposition) against the full 10x10
     decomposition every iteration (psd="full", the round-1 solver) on the same batch: same statuses, same number
-    of poses, same poses, about the same iteration counts."""
+    of poses, same poses, about the same iteration counts.  psd="track": two threads per problem (pnpl_track2.cuh, the
+    default); "track1": one thread per problem."""
     from cvxpnpl_b200 import synth
     d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=1234)
     a = _solve(cb, d, n_pts, n_lines, psd="full")
-    w = _solve(cb, d, n_pts, n_lines, psd="track")
+    w = _solve(cb, d, n_pts, n_lines, psd=psd)
     assert w.launches == a.launches + 2          # solve_track_kernel + redecomp_kernel really ran
     sa, sw = (a.status & 0xFF).cpu().numpy(), (w.status & 0xFF).cpu().numpy()
     na, nw = a.n_poses.cpu().numpy(), w.n_poses.cpu().numpy()

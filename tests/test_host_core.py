@@ -219,3 +219,22 @@ def test_host_tracked_psd_matches_full_decomposition(n_pts, n_lines, B):
         assert np.linalg.norm(to - w["t"][i, 0]) / np.linalg.norm(to) < 1e-6
         checked += 1
     assert checked == 3
+
+
+@pytest.mark.parametrize("n_pts,n_lines,B", [(8, 4, 300), (0, 6, 300), (4, 0, 100)])
+def test_host_two_threads_per_problem_matches_one(n_pts, n_lines, B):
+    """pnpl_track2.cuh (the tracked solver with every step of an iteration split between two threads, here two host
+    threads and a spinning barrier where the kernel has its barriers) against pnpl_track.cuh: same statuses, same
+    hand-backs, same poses; iteration counts differ by the summation order of the split dot products only."""
+    d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=78)
+    a = harness.solve_track(d)
+    w = harness.solve_track(d, two=True)
+    sa, sw = a["status"] & 0xFF, w["status"] & 0xFF
+    assert (sa != sw).mean() <= 0.02
+    assert abs(int(a["fallbacks"].sum()) - int(w["fallbacks"].sum())) <= max(2, 0.1 * a["fallbacks"].sum())
+    ok = (sa == 0) & (sw == 0) & (a["n_poses"] == 1) & (w["n_poses"] == 1)
+    assert ok.mean() > (0.95 if n_pts + n_lines > 4 else 0.4)
+    ang = synth.rotation_angle(a["R"][ok, 0], w["R"][ok, 0])
+    terr = np.linalg.norm(a["t"][ok, 0] - w["t"][ok, 0], axis=1) / np.linalg.norm(a["t"][ok, 0], axis=1)
+    assert ang.max() < 1e-6 and terr.max() < 1e-6
+    assert abs(w["iters"][ok].mean() - a["iters"][ok].mean()) <= 0.03 * a["iters"][ok].mean() + 1
