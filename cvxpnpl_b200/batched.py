@@ -228,8 +228,10 @@ def pnpl_batched(pts_2d, line_2d, pts_3d, line_3d, K, **kw) -> BatchedPoses:
 # ---- stage entry points (parity tests of the individual reference functions) ----
 
 
-def assemble_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None):
-    """-> Q [B,9,9] (= A'A, cvxpnpl.py:475) and Bmat [B,3,9] (cvxpnpl.py:623)."""
+def assemble_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None, staging="tma"):
+    """-> Q [B,9,9] (= A'A, cvxpnpl.py:475) and Bmat [B,3,9] (cvxpnpl.py:623).  With >= 256 correspondences per problem
+    the assembly is a streaming reduction; staging="tma" (default) stages the point slabs through shared memory with
+    bulk-asynchronous copies, "loads" keeps the plain-load kernel (A/B measurements)."""
     _require_cuda()
     lib = _lib.load()
     device = torch.device("cuda", torch.cuda.current_device())
@@ -246,6 +248,9 @@ def assemble_batched(K, pts_2d=None, pts_3d=None, line_2d=None, line_3d=None):
     d.batch, d.k_batched, d.K = B, int(K.dim() == 3), _ptr(K)
     d.pts_2d, d.pts_3d = _ptr(pts_2d if have_p else None), _ptr(pts_3d if have_p else None)
     d.line_2d, d.line_3d = _ptr(line_2d if have_l else None), _ptr(line_3d if have_l else None)
+    if staging not in ("tma", "loads"):
+        raise ValueError("staging must be 'tma' or 'loads'")
+    d.psd_mode = 0 if staging == "tma" else 1
     Q = torch.empty((B, 9, 9), dtype=torch.float64, device=device)
     Bm = torch.empty((B, 3, 9), dtype=torch.float64, device=device)
     stream = torch.cuda.current_stream(device).cuda_stream

@@ -463,18 +463,26 @@ def test_large_n_assembly(cb):
     against ground truth."""
     from cvxpnpl_b200 import synth
     from oracle import cvxpnpl_oracle as orc
-    for n_pts, n_lines in ((1000, 0), (5000, 300), (0, 9000)):
+    # staging="tma": the point slabs go through shared memory with bulk-asynchronous copies (accumulate_tma_kernel:
+    # even point counts; 1537 = one full tile ring + a ragged last tile, odd -> the plain-load kernel takes the points);
+    # "loads": the plain-load kernel.  Both against the oracle, and against each other.
+    for n_pts, n_lines in ((1000, 0), (5000, 300), (0, 9000), (1537, 0), (3074, 0), (512, 256), (20000, 0)):
         d = synth.make_batch(3, n_pts, n_lines, noise=1.0, seed=51)
-        Q, Bm = cb.assemble_batched(d["K"], d["pts_2d"] if n_pts else None, d["pts_3d"] if n_pts else None,
-                                    d["line_2d"] if n_lines else None, d["line_3d"] if n_lines else None)
-        torch.cuda.synchronize()
-        for i in range(3):
-            C, N = orc._stack(d["pts_2d"][i] if n_pts else None, d["pts_3d"][i] if n_pts else None,
-                              d["line_2d"][i] if n_lines else None, d["line_3d"][i] if n_lines else None, d["K"])
-            A, B = orc.reduce_translation(C, N)
-            ref = A.T @ A
-            assert np.abs(Q[i].cpu().numpy() - ref).max() < 1e-11 * np.abs(ref).max()
-            assert np.allclose(Bm[i].cpu().numpy(), B, rtol=1e-9, atol=1e-11)
+        got = {}
+        for staging in ("tma", "loads"):
+            Q, Bm = cb.assemble_batched(d["K"], d["pts_2d"] if n_pts else None, d["pts_3d"] if n_pts else None,
+                                        d["line_2d"] if n_lines else None, d["line_3d"] if n_lines else None,
+                                        staging=staging)
+            torch.cuda.synchronize()
+            got[staging] = (Q.cpu().numpy(), Bm.cpu().numpy())
+            for i in range(3):
+                C, N = orc._stack(d["pts_2d"][i] if n_pts else None, d["pts_3d"][i] if n_pts else None,
+                                  d["line_2d"][i] if n_lines else None, d["line_3d"][i] if n_lines else None, d["K"])
+                A, B = orc.reduce_translation(C, N)
+                ref = A.T @ A
+                assert np.abs(got[staging][0][i] - ref).max() < 1e-11 * np.abs(ref).max()
+                assert np.allclose(got[staging][1][i], B, rtol=1e-9, atol=1e-11)
+        assert np.abs(got["tma"][0] - got["loads"][0]).max() <= 1e-13 * np.abs(got["loads"][0]).max()
     d = synth.make_batch(40, 2000, 0, noise=1.0, seed=52)
     res = _solve(cb, d, 2000, 0)
     assert ((res.status & 0xFF) == 0).all() and (res.n_poses == 1).all()
