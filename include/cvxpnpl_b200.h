@@ -89,8 +89,10 @@ typedef struct cvxpnpl_b200_desc {
     int32_t skip_prepass;   /* != 0: the pre-pass of every problem has been run by cvxpnpl_b200_prepass already */
     int32_t psd_mode;       /* PSD projection of the ADMM iteration.  0 = default: two tracked eigenpairs refined once per
                                iteration, with a Cholesky certificate that nothing else in the spectrum is positive (problems
-                               that fail it are finished with the full decomposition); 1 = full 10x10 eigen-decomposition
-                               (warm-started Jacobi sweep) every iteration */
+                               that fail it for good are finished with the full decomposition), two threads per problem;
+                               1 = full 10x10 eigen-decomposition (warm-started Jacobi sweep) every iteration, one thread
+                               per problem (the round-1 solver; in `assemble`: the plain-load large-n kernel);
+                               2 = tracked eigenpairs, one thread per problem */
     /* ---- packed output (optional) ---- */
     double* record;         /* optional [B, 15]: R of candidate 0 (9, row-major) | t (3) | n_poses | status | iters,
                                written by the finish kernel next to R / t: the row a multi-GPU caller all-gathers
@@ -125,7 +127,9 @@ int cvxpnpl_b200_prepass(const cvxpnpl_b200_desc* desc, int64_t first, int64_t c
 int cvxpnpl_b200_kernel_times(float* ms, int n);
 
 /* Stage: correspondences -> Q [B,9,9] (= A'A of cvxpnpl.py:475) and Bmat [B,3,9]
- * (cvxpnpl.py:623).  Uses the problem fields of desc only. */
+ * (cvxpnpl.py:623).  Uses the problem fields of desc (and psd_mode, see there).  From 256 correspondences per problem
+ * the assembly is a streaming reduction; point slabs that are 16-byte aligned (even point count) are staged through
+ * shared memory with TMA bulk copies. */
 int cvxpnpl_b200_assemble(const cvxpnpl_b200_desc* desc, double* Q, double* Bmat, void* stream);
 
 /* Stage: Q [B,9,9] -> Z [B,10,10] (desc->Z), iterations (desc->iters), status,
