@@ -402,7 +402,7 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
     G[55] = 0.0;   // zero pad read by the 8-word chunks of aa_step (neither the step nor the Cholesky scratch reach it)
     const cvx::AnyLane any;
     int64_t b = -1;
-    bool exhausted = false;
+    bool exhausted = false, dry_known = false;
     int drain = 0;
     bool counted = false;
     const unsigned long long n_work = (unsigned long long)d.batch;
@@ -439,7 +439,7 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
         if (__syncthreads_and(b < 0)) break;
         bool give_up = false;
         if (grace >= 0 && b >= 0 && st.iterating) {
-            if (drain > 0 || *(volatile int*)&queue_dry) {
+            if (drain > 0 || dry_known) {
                 if (!counted) {
                     atomicAdd(ctrl + CTRL_ACTIVE, 1ULL);
                     counted = true;
@@ -450,6 +450,8 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
         }
         bool want = false;
         if (b >= 0 && !give_up) want = cvx::track_pass_dr(o, M, G, U, TH, QR, st);
+        __syncwarp();
+        dry_known = *(volatile int*)&queue_dry != 0;   // for the next pass (the flag is set in front of the barrier)
         __syncwarp();
         if (H.any(want)) cvx::aa_step(M, G, H, st.aa, want, wslot, (float)st.res_prev);
         wslot = (wslot + 1 == cvx::AA_M) ? 0 : wslot + 1;
@@ -538,7 +540,7 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
     }
     if (ROLE == 0) G[55] = 0.0;
     int64_t b = -1;
-    bool exhausted = false, counted = false;
+    bool exhausted = false, counted = false, dry_known = false;
     int drain = 0;
     const unsigned long long n_work = (unsigned long long)d.batch;
     cvx::LaneState st;
@@ -573,7 +575,7 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
                     }
                 }
             } else if (grace >= 0 && st.iterating) {
-                if (drain > 0 || *(volatile int*)queue_dry) {
+                if (drain > 0 || dry_known) {
                     if (!counted) {
                         atomicAdd(ctrl + CTRL_ACTIVE, 1ULL);
                         counted = true;
@@ -586,6 +588,7 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
             X[cvx::X2_CTL] = ctl;
         }
         if (cta_vote_and(b < 0)) break;
+        dry_known = *(volatile int*)queue_dry != 0;   // (read behind the barrier: the flag is set in front of it)
         const double ctl = X[cvx::X2_CTL];
         if (ROLE == 1 && b < 0 && ctl >= 0.0) {
             b = (int64_t)ctl;
@@ -1452,7 +1455,7 @@ Opts make_opts(const cvxpnpl_b200_desc* d)
     o.anderson = d->anderson >= 0;
     o.aa_on2 = cvx::AA_RES2_ON;
     o.rowk = (d->variant == 1) ? 0.0 : 1.0;
-    o.kappa = cvx::DUAL_GUESS;
+    o.kappa = cvx::default_kappa(d->n_pts);
     o.max_iters = d->max_iters > 0 ? d->max_iters : 2500;
     o.sweeps = d->sweeps > 0 ? d->sweeps : 1;
     o.early = cvx::default_early(d->n_pts, d->n_lines);

@@ -30,7 +30,7 @@ extern "C" int host_solve(int64_t B, int n_pts, int n_lines, const double* K, in
     cvx::default_params(n_pts, o.rho_rel, o.alpha, o.sigma);
     o.anderson = anderson != 0;
     o.rowk = variant == 1 ? 0.0 : 1.0;
-    o.kappa = cvx::DUAL_GUESS;
+    o.kappa = cvx::default_kappa(n_pts);
     o.early = cvx::default_early(n_pts, n_lines);
     o.aa_on2 = (anderson > 1) ? (1e-3 * anderson) * (1e-3 * anderson) : cvx::AA_RES2_ON;   // test hook: threshold in 1e-3 units
     std::vector<double> V(100), M(56), T(56), L(10), qr(45);   // T[55] = 0: zero pad for aa_step
@@ -140,7 +140,7 @@ extern "C" int host_solve_track(int64_t B, int n_pts, int n_lines, const double*
     cvx::default_params(n_pts, o.rho_rel, o.alpha, o.sigma);
     o.anderson = anderson != 0;
     o.rowk = variant == 1 ? 0.0 : 1.0;
-    o.kappa = cvx::DUAL_GUESS;
+    o.kappa = cvx::default_kappa(n_pts);
     o.aa_on2 = cvx::AA_RES2_ON;
     o.early = cvx::default_early(n_pts, n_lines);
     std::vector<double> V(100), M(56), T(56), L(10), qr(45), U(20), TH(2), BS(36), Qs(45), Bs(27);
@@ -383,7 +383,7 @@ extern "C" int host_solve_track2(int64_t B, int n_pts, int n_lines, const double
     cvx::default_params(n_pts, o.rho_rel, o.alpha, o.sigma);
     o.anderson = anderson != 0;
     o.rowk = variant == 1 ? 0.0 : 1.0;
-    o.kappa = cvx::DUAL_GUESS;
+    o.kappa = cvx::default_kappa(n_pts);
     o.aa_on2 = cvx::AA_RES2_ON;
     o.early = cvx::default_early(n_pts, n_lines);
     Shared2 sh;

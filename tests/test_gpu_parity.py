@@ -418,7 +418,9 @@ def test_batched_synth_suite(cb):
     cell = suite.run_cell("pnl", 4, 0.0, 2000, seed=3)          # minimal-ish: several candidates
     # (the share of multi-candidate results shrinks as convergence improves: most rank-2 results
     # of 4-line problems are iterates that stopped at the cap)
-    assert cell.multi > 0.01 and cell.ang_median_deg < 1e-3
+    # (0.045 in round 1; 0.0045 with the dual guess kappa = 0.9 for small problems, which took the 4-line problems
+    # at the cap from 2 % to 0.5 %)
+    assert cell.multi > 0.001 and cell.ang_median_deg < 1e-3
 
 
 def test_rc_variant(cb, golden):

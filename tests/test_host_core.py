@@ -205,6 +205,9 @@ def test_host_tracked_psd_matches_full_decomposition(n_pts, n_lines, B):
     # well-posed families are tracked from start to end (no hand-back); minimal ones often need a third eigenpair
     if n_pts >= 8:
         assert w["fallbacks"].mean() <= 0.03
+    if n_pts + n_lines <= 4:
+        return   # minimal sets: the optimal face need not be a point, another solver may land elsewhere on it
+                 # (those families are compared as candidate SETS on the same Z: test_extraction_degenerate)
     checked = 0
     for i in np.flatnonzero(ok & (w["fallbacks"] == 0))[:3]:
         with warnings.catch_warnings():
