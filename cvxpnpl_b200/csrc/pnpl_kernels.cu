@@ -35,6 +35,7 @@ constexpr int N_BUCKETS = 64;              // difficulty buckets of the work que
 constexpr int SMEM_DOUBLES = 221;          // V 100 + M 55 + T 55 (+1 zero pad) + lambda 10
 constexpr size_t SMEM_BYTES = (size_t)NT * SMEM_DOUBLES * sizeof(double);
 
+constexpr int MAX_DEVICES_SIDE = 64;
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 
@@ -57,6 +58,29 @@ void mark(bool on, int slot, cudaStream_t st)
     g_ev_slot[g_ev_n] = slot;
     cudaEventRecord(g_ev[g_ev_n], st);
     ++g_ev_n;
+}
+
+// side stream + fork/join events of the concurrent service kernel: one set per host thread and device
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+thread_local SideStream g_side[MAX_DEVICES_SIDE];
+SideStream* side_for_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES_SIDE) return nullptr;
+    SideStream& s = g_side[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            s = SideStream();
+            return nullptr;
+        }
+    }
+    return &s;
 }
 
 int fail(int code, const char* msg)
@@ -227,7 +251,10 @@ enum {
     CTRL_NEXT = 0, CTRL_NSTRAG = 1, CTRL_STRAG_NEXT = 2, CTRL_RESUME_NEXT = 3, CTRL_NEXT32 = 4, CTRL_ACTIVE = 5,
     CTRL_NFAIL = 6,      // problems the tracked solver handed back (failed certificate / stragglers): length of fail_list
     CTRL_FAIL_NEXT = 7,  // queue head of the full-decomposition solver working on that list
-    CTRL_TRK_NEXT = 8    // queue head of the tracked solver
+    CTRL_TRK_NEXT = 8,   // queue head of the tracked solver
+    CTRL_TRK_DONE = 9,   // CTAs of the tracked solver that have finished (the concurrent service kernel stops then)
+    CTRL_SVC_NEXT = 10,  // tickets (entries of fail_list) taken by the concurrent service kernel
+    CTRL_NSTRAG_START = 11   // slab entries that exist when straggler_kernel starts (snapshot of CTRL_NSTRAG)
 };
 
 // RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
@@ -292,13 +319,17 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
     cvx::aa_reset(st.aa);
     int wslot = 0;   // warp-uniform history column
     for (;;) {
-        if (b < 0 && !exhausted) {
+        while (b < 0 && !exhausted) {
             const unsigned long long nb = atomicAdd(ctrl + q_next, 1ULL);
             if (nb < n_work) {
                 if (RESUME) {
                     b = cvx::problem_resume(slab + nb * cvx::HAND_DOUBLES, V, M, L, QR, st);
                 } else {
                     b = (int64_t)order[nb];   // queue position -> problem (likely stragglers first)
+                    if (b < 0) {              // (hand-back list: served by the concurrent service kernel already)
+                        b = -1;
+                        continue;
+                    }
                     if (warm) {   // the FP32 first phase / the tracked solver has already advanced the problem
                         cvx::problem_begin_warm(pre + b * cvx::PRE_DOUBLES, warm + b * cvx::WARM_DOUBLES, o, V, M, L, QR,
                                                 st);
@@ -461,8 +492,11 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
                 cvx::track_park(o, U, TH, st, park + b * cvx::PARK_DOUBLES, d.iters + b);
                 b = -1;
             } else if (rc < 0) {
+                // record first, then the list entry the concurrent service kernel may be waiting for
                 cvx::track_handoff(M, QR, st, pre + b * cvx::PRE_DOUBLES);
-                fail_list[atomicAdd(ctrl + CTRL_NFAIL, 1ULL)] = (int32_t)b;
+                __threadfence();
+                *(volatile int32_t*)(fail_list + atomicAdd(ctrl + CTRL_NFAIL, 1ULL)) = (int32_t)b;
+                __threadfence();
                 b = -1;
                 if (give_up) exhausted = true;
             }
@@ -471,6 +505,10 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
                 counted = false;
             }
         }
+    }
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(ctrl + CTRL_TRK_DONE, 1ULL);
     }
     tmem_free_all(tmem_base);
 }
@@ -514,10 +552,14 @@ __device__ __forceinline__ bool cta_vote_and(bool f)
 
 // (one function for both roles, the role a run-time value: everything the two threads of a problem do alike -- most of a
 // pass -- is then the SAME instructions for all eight warps, which walk them in lock-step out of one instruction stream)
+#ifndef CVX_SLOW_IT
+#define CVX_SLOW_IT 100
+#endif
+constexpr int SLOW_IT = CVX_SLOW_IT;
 __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_desc& d, const Opts& o, unsigned long long* ctrl,
                                             double* pre, double* park, const double* warm, const int32_t* order,
-                                            int32_t* fail_list, int grace, int handoff_max, double* smem, uint32_t tmem_base,
-                                            int* queue_dry)
+                                            int32_t* fail_list, int grace, int handoff_max, bool svc_on, double* smem,
+                                            uint32_t tmem_base, int* queue_dry)
 {
     const int p = threadIdx.x & (NT - 1);
     const int wq = (threadIdx.x >> 5) & 3;
@@ -584,6 +626,11 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
                 }
                 if (drain > grace && *(volatile unsigned long long*)(ctrl + CTRL_ACTIVE) <= (unsigned long long)handoff_max)
                     ctl = -3.0;
+                // a slow problem moves to the concurrent service kernel (a warp of its own: ~6.5 us per iteration
+                // instead of one ~12 us pass) if a service warp is waiting for work right now
+                if (svc_on && st.it >= SLOW_IT && st.it % 25 == 0 &&
+                    *(volatile unsigned long long*)(ctrl + CTRL_SVC_NEXT) > *(volatile unsigned long long*)(ctrl + CTRL_NFAIL))
+                    ctl = -3.0;
             }
             X[cvx::X2_CTL] = ctl;
         }
@@ -615,9 +662,12 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
                 b = -1;
             } else if (rc < 0) {
                 if (ROLE == 0) {
+                    // record first, then the list entry the concurrent service kernel may be waiting for
                     cvx::track_handoff(M, QR, st, pre + b * cvx::PRE_DOUBLES);
-                    fail_list[atomicAdd(ctrl + CTRL_NFAIL, 1ULL)] = (int32_t)b;
-                    if (give_up) exhausted = true;
+                    __threadfence();
+                    *(volatile int32_t*)(fail_list + atomicAdd(ctrl + CTRL_NFAIL, 1ULL)) = (int32_t)b;
+                    __threadfence();
+                    if (give_up && drain > 0) exhausted = true;
                 }
                 b = -1;
             }
@@ -631,15 +681,19 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
 
 __global__ void __launch_bounds__(NT2, 1)
 solve_track2_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double* pre, double* park, const double* warm,
-                    const int32_t* order, int32_t* fail_list, int grace, int handoff_max)
+                    const int32_t* order, int32_t* fail_list, int grace, int handoff_max, int svc_on)
 {
     extern __shared__ double smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ int queue_dry;
     if (threadIdx.x == 0) queue_dry = 0;
     const uint32_t tmem_base = tmem_alloc_all(&tmem_slot);
-    track2_loop(threadIdx.x < NT ? 0 : 1, d, o, ctrl, pre, park, warm, order, fail_list, grace, handoff_max, smem, tmem_base,
-                &queue_dry);
+    track2_loop(threadIdx.x < NT ? 0 : 1, d, o, ctrl, pre, park, warm, order, fail_list, grace, handoff_max, svc_on != 0, smem,
+                tmem_base, &queue_dry);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctrl + CTRL_TRK_DONE, 1ULL);
+    }
     tmem_free_all(tmem_base);
 }
 
@@ -656,6 +710,7 @@ __global__ void __launch_bounds__(NT_R) redecomp_kernel(const unsigned long long
     for (unsigned long long k = (unsigned long long)blockIdx.x * NT_R + tid; k < ctrl[CTRL_NFAIL];
          k += (unsigned long long)gridDim.x * NT_R) {
     const int64_t b = fail_list[k];
+    if (b < 0) continue;   // served by the concurrent service kernel
     const double* rec = pre + b * cvx::PRE_DOUBLES;
     double* w = warm + b * cvx::WARM_DOUBLES;
     cvx::Arr<NT_R> V{smem + tid};
@@ -755,10 +810,75 @@ __global__ void __launch_bounds__(128) ortho_kernel(int64_t batch, double* warm)
 // ---------------------------------------------------------------------------------
 constexpr int NT_W = 256;
 constexpr size_t SMEM_W_BYTES = (NT_W / 32) * sizeof(cvx::WarpSmem);
+// One handed-back problem solved by one warp: iterate M, Q/rho, rho and the iteration count from the problem's
+// tracked record (read past L1: another SM may just have written it), eigen-decomposition by a warp-cooperative cold
+// Jacobi, DR loop to the end; the result goes into a fresh slab entry (flag "DR loop finished") for the resume kernel.
+__device__ __forceinline__ void warp_serve_record(cvx::WarpSmem& S, const Opts& o, int lane, const uint32_t pk[9],
+                                                  unsigned long long* ctrl, const double* rec, int64_t b, double* slab,
+                                                  int it_cap, unsigned n_track_ctas = 0, unsigned long long n_warps = 0)
+{
+    for (int e = lane; e < 100; e += 32) {
+        const int r = e / 10, c = e - 10 * r;
+        S.M[e] = __ldcg(rec + cvx::TR_M + cvx::sidx(r, c));
+        S.Q[e] = (r < 9 && c < 9) ? __ldcg(rec + cvx::TR_Q + cvx::sidx(r, c)) : 0.0;
+    }
+    for (int e = lane; e < 56; e += 32) {
+        S.gp[e] = S.sp[e] = S.gk[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < cvx::AA_M; ++j) S.dG[j][e] = S.dS[j][e] = 0.f;
+    }
+    if (lane < cvx::AA_GRAM_WORDS) S.gram[lane] = 0.f;
+    if (lane < 16) S.dots[lane] = 0.f;
+    int it = (int)__ldcg(rec + cvx::TR_IT);
+    double rho = __ldcg(rec + cvx::TR_RHO);
+    const int fl = (int)__ldcg(rec + cvx::TR_FLAGS);
+    __syncwarp();
+    cvx::warp_cold_decompose(S, lane, pk);
+    bool converged = (fl & 2) != 0;
+    bool over = (fl & 1) != 0;
+    if (!over) {
+        // it_cap > 0: the concurrent service kernel lends its warp for that many iterations at most, in chunks of 100;
+        // a problem that needs more (a cap runner), or whose warp should leave because the bulk of the batch is over
+        // and a long hand-back list is waiting for the wider kernels anyway, is left unfinished in the slab (flags 0)
+        // and goes on in straggler_kernel
+        const int last = (it_cap > 0 && it + it_cap < o.max_iters) ? it + it_cap : o.max_iters;
+        for (;;) {
+            const int stop = (it_cap > 0 && it + 100 < last) ? it + 100 : last;
+            cvx::warp_dr_loop(S, o, lane, it, converged, rho, stop);
+            over = converged || it >= o.max_iters;
+            if (over || it >= last) break;
+            int leave = 0;
+            if (lane == 0)
+                leave = *(volatile unsigned long long*)(ctrl + CTRL_TRK_DONE) >= (unsigned long long)n_track_ctas &&
+                        *(volatile unsigned long long*)(ctrl + CTRL_NFAIL) > n_warps;
+            if (__shfl_sync(0xffffffffu, leave, 0)) break;
+        }
+    }
+    unsigned long long ks = 0;
+    if (lane == 0) ks = atomicAdd(ctrl + CTRL_NSTRAG, 1ULL);
+    ks = __shfl_sync(0xffffffffu, ks, 0);
+    double* h = slab + ks * cvx::HAND_DOUBLES;
+    for (int p = lane; p < 55; p += 32) {
+        int r, c;
+        cvx::unpack_idx(p, r, c);
+        h[cvx::HO_M + p] = S.M[r * 10 + c];
+        if (r < 9) h[cvx::HO_Q + p] = S.Q[r * 10 + c];
+    }
+    for (int e = lane; e < 100; e += 32) h[cvx::HO_V + e] = S.V[e];
+    if (lane < 10) h[cvx::HO_L + lane] = S.L[lane];
+    if (lane == 0) {
+        h[cvx::HO_IT] = (double)it;
+        h[cvx::HO_RHO] = rho;
+        h[cvx::HO_FLAGS] = (converged ? 1.0 : 0.0) + (over ? 2.0 : 0.0);   // 2: the DR loop is over
+        h[cvx::HO_B] = (double)b;
+    }
+    __syncwarp();
+}
+
 // DIRECT mode (fail_list != nullptr and the tracked solver handed back no more problems than there are warps here,
-// `direct_max`): the entries are taken straight from the tracked solver's hand-back list -- iterate M, Q/rho, rho and
-// the iteration count from the problem's record, eigen-decomposition by a warp-cooperative cold Jacobi -- instead of
-// going through redecomp_kernel and one pass of the thread solver first (~0.17 ms of latency for a handful of problems).
+// `direct_max`): the entries are taken straight from the tracked solver's hand-back list (warp_serve_record) instead
+// of going through redecomp_kernel and one pass of the thread solver first (~0.17 ms of latency for a handful of
+// problems).  Entries the concurrent service kernel has already finished are marked (fail_list < -1) / flagged.
 __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned long long* ctrl, double* slab,
                                                             const int32_t* fail_list, const double* pre, int direct_max)
 {
@@ -767,7 +887,10 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
     const int lane = threadIdx.x & 31;
     const unsigned long long n_fail = fail_list ? ctrl[CTRL_NFAIL] : 0ULL;
     const bool direct = n_fail > 0 && n_fail <= (unsigned long long)direct_max;
-    const unsigned long long n = direct ? n_fail : ctrl[CTRL_NSTRAG];
+    // tickets: first the slab entries that exist when this kernel starts (hand-overs of the thread solver; problems the
+    // service kernel gave back unfinished), then -- DIRECT mode -- the entries of the hand-back list nobody has served
+    const unsigned long long n_slab = *(volatile unsigned long long*)(ctrl + CTRL_NSTRAG_START);
+    const unsigned long long n = n_slab + (direct ? n_fail : 0ULL);
     uint32_t pk[9];
     cvx::sweep_tables(lane, pk);
     for (;;) {
@@ -775,37 +898,21 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
         if (lane == 0) k = atomicAdd(ctrl + CTRL_STRAG_NEXT, 1ULL);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n) break;
-        double* h = slab + k * cvx::HAND_DOUBLES;
-        bool dr_over = false, conv_in = false;
-        if (direct) {
-            const int64_t b = fail_list[k];
-            const double* rec = pre + b * cvx::PRE_DOUBLES;
-            for (int e = lane; e < 100; e += 32) {
-                const int r = e / 10, c = e - 10 * r;
-                S.M[e] = rec[cvx::TR_M + cvx::sidx(r, c)];
-                S.Q[e] = (r < 9 && c < 9) ? rec[cvx::TR_Q + cvx::sidx(r, c)] : 0.0;
-            }
-            const int fl = (int)rec[cvx::TR_FLAGS];
-            dr_over = (fl & 1) != 0;
-            conv_in = (fl & 2) != 0;
-            if (lane == 0) {
-                h[cvx::HO_IT] = rec[cvx::TR_IT];
-                h[cvx::HO_RHO] = rec[cvx::TR_RHO];
-                h[cvx::HO_B] = (double)b;
-                if (k == 0) ctrl[CTRL_NSTRAG] = n_fail;   // what the resume kernel (next launch) works through
-            }
-            __syncwarp();
-            cvx::warp_cold_decompose(S, lane, pk);
-        } else {
-            // slab entry -> full-form matrices in shared memory
-            for (int e = lane; e < 100; e += 32) {
-                const int r = e / 10, c = e - 10 * r;
-                S.M[e] = h[cvx::HO_M + cvx::sidx(r, c)];
-                S.V[e] = h[cvx::HO_V + e];
-                S.Q[e] = (r < 9 && c < 9) ? h[cvx::HO_Q + cvx::sidx(r, c)] : 0.0;
-            }
-            if (lane < 10) S.L[lane] = h[cvx::HO_L + lane];
+        if (k >= n_slab) {
+            const int64_t b = fail_list[k - n_slab];
+            if (b >= 0) warp_serve_record(S, o, lane, pk, ctrl, pre + b * cvx::PRE_DOUBLES, b, slab, 0);
+            continue;
         }
+        double* h = slab + k * cvx::HAND_DOUBLES;
+        if (((int)h[cvx::HO_FLAGS] & 2) != 0) continue;   // finished by the service kernel already
+        // slab entry -> full-form matrices in shared memory
+        for (int e = lane; e < 100; e += 32) {
+            const int r = e / 10, c = e - 10 * r;
+            S.M[e] = h[cvx::HO_M + cvx::sidx(r, c)];
+            S.V[e] = h[cvx::HO_V + e];
+            S.Q[e] = (r < 9 && c < 9) ? h[cvx::HO_Q + cvx::sidx(r, c)] : 0.0;
+        }
+        if (lane < 10) S.L[lane] = h[cvx::HO_L + lane];
         for (int e = lane; e < 56; e += 32) {
             S.gp[e] = S.sp[e] = S.gk[e] = 0.f;
 #pragma unroll
@@ -816,8 +923,8 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
         int it = (int)h[cvx::HO_IT];
         double rho = h[cvx::HO_RHO];
         __syncwarp();
-        bool converged = conv_in;
-        if (!dr_over) cvx::warp_dr_loop(S, o, lane, it, converged, rho, o.max_iters);
+        bool converged = false;
+        cvx::warp_dr_loop(S, o, lane, it, converged, rho, o.max_iters);
         for (int p = lane; p < 55; p += 32) {
             int r, c;
             cvx::unpack_idx(p, r, c);
@@ -829,9 +936,70 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
         if (lane == 0) {
             h[cvx::HO_IT] = (double)it;
             h[cvx::HO_RHO] = rho;
-            h[cvx::HO_FLAGS] = converged ? 1.0 : 0.0;
+            h[cvx::HO_FLAGS] = (converged ? 1.0 : 0.0) + 2.0;
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Concurrent service kernel: runs on a side stream BESIDE the persistent tracked solver, on the SMs that kernel's
+// (smaller) grid leaves free, and finishes the problems the tracked solver hands back WHILE the bulk of the batch is
+// still being solved -- the problems whose certificate failed, and the slow ones (more than SLOW_IT iterations) as
+// long as the service has warps to spare.  Warp per problem (warp_serve_record); a warp takes a ticket, waits for
+// that entry of fail_list to be published (the list is initialised to -1), solves it, marks the entry served
+// (-2 - b).  When every CTA of the tracked solver has finished, the warps finish what they hold and leave; whatever
+// is still unserved goes through the kernels after this one as before.  A wall-clock limit guards the wait.
+// ---------------------------------------------------------------------------------
+constexpr int NT_SVC = 512;
+constexpr int N_SVC_CTAS = 2;
+constexpr int SVC_ITERS = 400;   // iterations a service warp spends on one problem
+constexpr size_t SMEM_SVC_BYTES = (NT_SVC / 32) * sizeof(cvx::WarpSmem);   // > half an SM: one CTA per SM
+__global__ void __launch_bounds__(NT_SVC, 1) service_kernel(Opts o, unsigned long long* ctrl, int32_t* fail_list, const double* pre,
+                                                            double* slab, unsigned n_track_ctas, unsigned long long limit_ns)
+{
+    extern __shared__ double smem[];
+    cvx::WarpSmem& S = reinterpret_cast<cvx::WarpSmem*>(smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    uint32_t pk[9];
+    cvx::sweep_tables(lane, pk);
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * (NT_SVC / 32);
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(ctrl + CTRL_SVC_NEXT, 1ULL);
+        k = __shfl_sync(FULL, k, 0);
+        int b = -1, leave = 0;
+        for (;;) {
+            if (lane == 0) {
+                b = *(volatile int32_t*)(fail_list + k);
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                const bool done = *(volatile unsigned long long*)(ctrl + CTRL_TRK_DONE) >= (unsigned long long)n_track_ctas ||
+                                  now - t0 > limit_ns;
+                if (done) {
+                    __threadfence();
+                    b = *(volatile int32_t*)(fail_list + k);   // published just before the last CTA finished?
+                    // the bulk is over: only a last handful of entries is still worth a warp here, anything more goes
+                    // to the (74 times wider) kernels after this one
+                    const unsigned long long n_pub = *(volatile unsigned long long*)(ctrl + CTRL_NFAIL);
+                    if (b < 0 || n_pub > k + n_warps) leave = 1;
+                }
+            }
+            b = __shfl_sync(FULL, b, 0);
+            leave = __shfl_sync(FULL, leave, 0);
+            if (b >= 0 || leave) break;
+            __nanosleep(1000);
+        }
+        if (leave) break;
+        __threadfence();
+        warp_serve_record(S, o, lane, pk, ctrl, pre + (int64_t)b * cvx::PRE_DOUBLES, b, slab, SVC_ITERS, n_track_ctas, n_warps);
+        if (lane == 0) {
+            __threadfence();
+            *(volatile int32_t*)(fail_list + k) = -2 - b;   // served (finished, or parked unfinished in the slab)
+        }
     }
 }
 
@@ -1554,6 +1722,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
                 e = cudaFuncSetAttribute(solve_track2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_TRK2_BYTES);
             if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(service_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SVC_BYTES);
+            if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(redecomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_R_BYTES);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(admm32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM32_BYTES);
@@ -1652,12 +1822,32 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         // ~6.7 us, and the detour (cold decomposition, hand-over, resume) costs ~0.3 ms: handing over earlier than 64
         // passes after the queue ran dry does not pay (1e5 PnPL 8+4: 1600 hand-overs at grace 40, 16 at 64).
         const int track_grace = d->handoff != 0 ? grace : 64;
+        // The concurrent service kernel (side stream): two SMs -- left free by a grid of n_sm - 2 CTAs when the batch
+        // fills the GPU -- finish handed-back problems warp per problem while the bulk is still being solved.
+        // desc.handoff < 0 (no warp-per-problem kernels at all) switches it off.
+        SideStream* side = (grace >= 0 && d->psd_mode != 2) ? side_for_current_device() : nullptr;
+        const bool svc_on = side != nullptr;
+        int64_t blocks_trk = blocks;
+        if (svc_on && blocks_trk > n_sm - N_SVC_CTAS) blocks_trk = n_sm - N_SVC_CTAS;
+        cudaMemsetAsync(fail_list, 0xFF, (size_t)d->batch * sizeof(int32_t), st);   // -1: entry not published yet
+        if (svc_on) {
+            cudaEventRecord(side->fork, st);
+            cudaStreamWaitEvent(side->stream, side->fork, 0);
+            service_kernel<<<N_SVC_CTAS, NT_SVC, SMEM_SVC_BYTES, side->stream>>>(o, ctrl, fail_list, pre, slab, (unsigned)blocks_trk,
+                                                                                 200000000ULL /* 0.2 s */);
+            ++g_launches;
+        }
         if (d->psd_mode == 2)   // one thread per problem (the round-2a form, kept for A/B runs)
-            solve_track_kernel<<<(unsigned)blocks, NT, SMEM_TRK_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order,
-                                                                             fail_list, track_grace, handoff_max);
+            solve_track_kernel<<<(unsigned)blocks_trk, NT, SMEM_TRK_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order,
+                                                                                 fail_list, track_grace, handoff_max);
         else
-            solve_track2_kernel<<<(unsigned)blocks, NT2, SMEM_TRK2_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order,
-                                                                                fail_list, track_grace, handoff_max);
+            solve_track2_kernel<<<(unsigned)blocks_trk, NT2, SMEM_TRK2_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order,
+                                                                                    fail_list, track_grace, handoff_max,
+                                                                                    svc_on ? 1 : 0);
+        if (svc_on) {
+            cudaEventRecord(side->join, side->stream);
+            cudaStreamWaitEvent(st, side->join, 0);
+        }
         mark(tm, 8, st);
         {
             const int64_t want_r = (d->batch + NT_R - 1) / NT_R, cap_r = n_sm * 4;   // grid-stride over the list
@@ -1675,6 +1865,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     }
     if (grace >= 0) {
         mark(tm, 4, st);
+        // snapshot of the slab's length: straggler_kernel allocates further entries while it runs
+        cudaMemcpyAsync(ctrl + CTRL_NSTRAG_START, ctrl + CTRL_NSTRAG, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st);
         straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab, tracked ? fail_list : nullptr, pre,
                                                                         direct_max);
         mark(tm, 5, st);

@@ -37,7 +37,7 @@ constexpr int HO_L = 155;      // 10 eigenvalues
 constexpr int HO_Q = 165;      // 45 packed Q / rho
 constexpr int HO_RHO = 210;
 constexpr int HO_IT = 211;
-constexpr int HO_FLAGS = 212;  // 1 = converged
+constexpr int HO_FLAGS = 212;  // bit 0: converged; bit 1: DR loop finished (by a warp-per-problem kernel)
 constexpr int HO_B = 213;      // problem index
 constexpr int HAND_DOUBLES = 216;
 
@@ -72,7 +72,7 @@ CVX_HD int64_t problem_resume(const double* h, Arr<S> V, Arr<S> M, Arr<S> L, QRT
     for (int e = 0; e < 45; ++e) QR[e] = h[HO_Q + e];
     st.rho = h[HO_RHO];
     st.it = (int32_t)h[HO_IT];
-    st.converged = h[HO_FLAGS] != 0.0;
+    st.converged = ((int)h[HO_FLAGS] & 1) != 0;   // (bit 1: the DR loop was finished by a warp)
     st.dobj = 0.0;
     st.phase = 1;
     st.finite = true;

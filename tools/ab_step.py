@@ -10,8 +10,9 @@ n_pts = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n_lines = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 psd = sys.argv[4] if len(sys.argv) > 4 else "track"
+seed = int(sys.argv[5]) if len(sys.argv) > 5 else 42
 dev = torch.device("cuda", 0)
-d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=42)
+d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=seed)
 K = torch.from_numpy(d["K"]).to(dev)
 args = {}
 if n_pts:
