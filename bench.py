@@ -410,10 +410,16 @@ def run_ours(a):
         return o
 
     def timed(fn, steps, warmup, marks=None):
+        import gc
         for _ in range(warmup):
             fn()
             flush.zero_()
         torch.cuda.synchronize()
+        # no cyclic-GC pause of the Python host inside the timed region (this process holds a few hundred thousand
+        # objects -- oracle poses, fixtures -- and a generation-2 collection takes 10-80 ms: seen as one slow step on
+        # BOTH ranks of a 2-GPU run, whose 2.7 ms strong-scaling steps leave the host no slack)
+        gc.collect()
+        gc.disable()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -428,12 +434,16 @@ def run_ours(a):
             e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
+        gc.enable()
         if marks is not None:
             marks.mark_end()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = sum(s.elapsed_time(e) for s, e in evs)
+        per = [s.elapsed_time(e) for s, e in evs]
+        ms = sum(per)
+        if per and max(per) > 2.0 * sorted(per)[len(per) // 2]:   # an outlier step: say so (stderr), the sum stands
+            print(f"[bench] rank {rank} {getattr(fn, '__name__', '?')}: per-step ms {[round(x, 2) for x in per]}", file=sys.stderr)
         if world > 1:
             tt = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -949,7 +949,8 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
 // long as the service has warps to spare.  Warp per problem (warp_serve_record); a warp takes a ticket, waits for
 // that entry of fail_list to be published (the list is initialised to -1), solves it, marks the entry served
 // (-2 - b).  When every CTA of the tracked solver has finished, the warps finish what they hold and leave; whatever
-// is still unserved goes through the kernels after this one as before.  A wall-clock limit guards the wait.
+// is still unserved goes through the kernels after this one as before.  A wall-clock limit (50 ms) guards the wait: under a
+// profiler that serialises kernels the service kernel runs alone, waits it out and leaves everything to those kernels.
 // ---------------------------------------------------------------------------------
 constexpr int NT_SVC = 512;
 constexpr int N_SVC_CTAS = 2;
@@ -1825,7 +1826,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         // The concurrent service kernel (side stream): two SMs -- left free by a grid of n_sm - 2 CTAs when the batch
         // fills the GPU -- finish handed-back problems warp per problem while the bulk is still being solved.
         // desc.handoff < 0 (no warp-per-problem kernels at all) switches it off.
-        SideStream* side = (grace >= 0 && d->psd_mode != 2) ? side_for_current_device() : nullptr;
+        static const bool no_service = getenv("CVXPNPL_B200_NO_SERVICE") != nullptr;   // (diagnostics)
+        SideStream* side = (grace >= 0 && d->psd_mode != 2 && !no_service) ? side_for_current_device() : nullptr;
         const bool svc_on = side != nullptr;
         int64_t blocks_trk = blocks;
         if (svc_on && blocks_trk > n_sm - N_SVC_CTAS) blocks_trk = n_sm - N_SVC_CTAS;
@@ -1834,7 +1836,7 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
             cudaEventRecord(side->fork, st);
             cudaStreamWaitEvent(side->stream, side->fork, 0);
             service_kernel<<<N_SVC_CTAS, NT_SVC, SMEM_SVC_BYTES, side->stream>>>(o, ctrl, fail_list, pre, slab, (unsigned)blocks_trk,
-                                                                                 200000000ULL /* 0.2 s */);
+                                                                                 50000000ULL /* 50 ms */);
             ++g_launches;
         }
         if (d->psd_mode == 2)   // one thread per problem (the round-2a form, kept for A/B runs)
