@@ -296,7 +296,15 @@ CVX_HD void jacobi_cs_fast(double app, double aqq, double apq, double& c, double
     const double g = fma(d, d, b2 * b2);
     const bool skip = !(fabs(apq) > 1e-18 * fabs(d)) || !(g > 1e-280);
     const float df = (float)d, bf = (float)b2;
+#if defined(__CUDA_ARCH__)
+    // device: MUFU reciprocal square root / reciprocal without the IEEE slow paths (the five chains of a round are the
+    // critical path of a warp's sweep: ~50 of ~190 instructions per round).  h = 0 (both |d| and |b| below 1e-19)
+    // gives NaN -> identity rotation: such a pivot is far below what the sweep resolves anyway.
+    const float h = fmaf(df, df, bf * bf);
+    float tf = __fdividef(copysignf(bf, bf * df), fabsf(df) + h * rsqrtf(h));
+#else
     float tf = copysignf(bf, bf * df) / (fabsf(df) + sqrtf(fmaf(df, df, bf * bf)));
+#endif
     tf = fminf(fmaxf(tf, -1.f), 1.f);        // |theta| <= pi/4; also catches 0/0-free overflow to inf
     const double t = skip || !(tf == tf) ? 0.0 : (double)tf;
     c = cvx_rsqrt(fma(t, t, 1.0));

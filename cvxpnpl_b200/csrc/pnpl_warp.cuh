@@ -278,6 +278,24 @@ __device__ __forceinline__ bool aa_solve_packed(const float* gram, const float* 
     return ok;
 }
 
+// Equality group g (0..14) of the affine projection as one lane applies it: the three entries it touches, their
+// coefficients and 1 / |a|^2 (times rowk for the row groups of the rc variant).
+struct AffLane {
+    int e0, e1, e2;
+    double s0, s1, a2, k;
+};
+__device__ __forceinline__ void aff_lane_init(AffLane& a, int g, const Opts& o, double isig, double inrm9)
+{
+    const signed char* t = c_triples[g];
+    a.e0 = t[0] * 10 + t[1];
+    a.e1 = t[3] * 10 + t[4];
+    a.e2 = t[6] * 10 + t[7];
+    a.s0 = t[2];
+    a.s1 = t[5];
+    a.a2 = (t[6] == 9) ? t[8] * isig : (double)t[8];
+    a.k = (t[6] == 9) ? inrm9 : (t[9] ? o.rowk * (1.0 / 3.0) : (1.0 / 3.0));
+}
+
 // DR iterations of one problem by one warp.  S holds M, V, L, Q (= Q/rho, full form
 // with a zero last row/column); `it` continues the problem's iteration count; the loop ends on
 // convergence or at iteration it_stop (<= o.max_iters).
@@ -299,6 +317,10 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
     double res_prev = 1e300;
     int32_t plat = 0;   // plateau detector (warp-uniform; restarts at the hand-over)
     converged = false;
+    // equality group of this lane (step 2), read from constant memory ONCE: inside the loop the fifteen lanes' table
+    // reads are fifteen serialised constant-cache accesses per entry (ncu, profiles/r2bf: ~1 k cycles per iteration)
+    AffLane af;
+    aff_lane_init(af, lane < 15 ? lane : 0, o, isig, inrm9);
     for (;;) {
         // ---- 1. Z = V max(L,0) V',  W = 2 Z - M - Q/rho  (W into X) -------------------
         {
@@ -310,8 +332,10 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
                 double z0 = 0.0, z1 = 0.0;
 #pragma unroll
                 for (int j = 0; j < 10; j += 2) {
-                    z0 = fma(lp[j] * S.V[r * 10 + j], S.V[c * 10 + j], z0);
-                    z1 = fma(lp[j + 1] * S.V[r * 10 + j + 1], S.V[c * 10 + j + 1], z1);
+                    // only the positive eigenpairs contribute (two or three of ten as a rule): warp-uniform branches,
+                    // and skipping a term that is exactly zero leaves the sum as it was
+                    if (lp[j] > 0.0) z0 = fma(lp[j] * S.V[r * 10 + j], S.V[c * 10 + j], z0);
+                    if (lp[j + 1] > 0.0) z1 = fma(lp[j + 1] * S.V[r * 10 + j + 1], S.V[c * 10 + j + 1], z1);
                 }
                 const double z = z0 + z1;
                 const double w = 2.0 * z - S.M[r * 10 + c] - S.Q[r * 10 + c];
@@ -326,18 +350,14 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
         double x0 = 0, x1 = 0, x2 = 0;
         int e0 = 0, e1 = 0, e2 = 0;
         if (lane < 15) {
-            const signed char* t = c_triples[lane];
-            e0 = t[0] * 10 + t[1];
-            e1 = t[3] * 10 + t[4];
-            e2 = t[6] * 10 + t[7];
-            const double s0 = t[2], s1 = t[5];
-            const double a2 = (t[6] == 9) ? t[8] * isig : (double)t[8];
+            e0 = af.e0;
+            e1 = af.e1;
+            e2 = af.e2;
             const double w0 = S.X[e0], w1 = S.X[e1], w2 = S.X[e2];
-            const double k = (t[6] == 9) ? inrm9 : (t[9] ? o.rowk * (1.0 / 3.0) : (1.0 / 3.0));
-            const double rr = (s0 * w0 + s1 * w1 + a2 * w2) * k;
-            x0 = w0 - s0 * rr;
-            x1 = w1 - s1 * rr;
-            x2 = w2 - a2 * rr;
+            const double rr = (af.s0 * w0 + af.s1 * w1 + af.a2 * w2) * af.k;
+            x0 = w0 - af.s0 * rr;
+            x1 = w1 - af.s1 * rr;
+            x2 = w2 - af.a2 * rr;
         } else if (lane >= 16 && lane < 25) {
             const int i = lane - 16, cc = i / 3, rr = i % 3;
             double R = 0, C = 0, G = 0;

@@ -11,8 +11,10 @@ n_lines = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 psd = sys.argv[4] if len(sys.argv) > 4 else "track"
 seed = int(sys.argv[5]) if len(sys.argv) > 5 else 42
+admm = os.environ.get("ADMM", "f64")
+noise = float(os.environ.get("NOISE", "1.0"))
 dev = torch.device("cuda", 0)
-d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=seed)
+d = synth.make_batch(B, n_pts, n_lines, noise=noise, seed=seed)
 K = torch.from_numpy(d["K"]).to(dev)
 args = {}
 if n_pts:
@@ -22,7 +24,7 @@ if n_lines:
 ws = cb.Workspace(B, dev)
 out = None
 for _ in range(3):
-    out = cb.solve_batched(K, **args, workspace=ws, out=out, psd=psd)
+    out = cb.solve_batched(K, **args, workspace=ws, out=out, psd=psd, admm_dtype=admm)
 torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ts = []
@@ -30,7 +32,7 @@ for _ in range(8):
     flush.zero_()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    out = cb.solve_batched(K, **args, workspace=ws, out=out, psd=psd, timing=True)
+    out = cb.solve_batched(K, **args, workspace=ws, out=out, psd=psd, timing=True, admm_dtype=admm)
     e.record()
     torch.cuda.synchronize()
     ts.append(s.elapsed_time(e))

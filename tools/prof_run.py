@@ -13,9 +13,10 @@ ap.add_argument("--batch", type=int, default=100000)
 ap.add_argument("--calls", type=int, default=2)
 ap.add_argument("--handoff", type=int, default=0)
 ap.add_argument("--admm", default="f64")
+ap.add_argument("--noise", type=float, default=1.0)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-d = synth.make_batch(a.batch, a.n_pts, a.n_lines, noise=1.0, seed=42)
+d = synth.make_batch(a.batch, a.n_pts, a.n_lines, noise=a.noise, seed=42)
 K = torch.from_numpy(d["K"]).to(dev)
 args = {}
 if a.n_pts:
