@@ -362,7 +362,7 @@ def measure_fp64_peak(device=None, iters=4000, repeats=5):
 
 
 KERNEL_NAMES = ("pre_kernel", "admm32_kernel", "ortho_kernel", "solve_fused_kernel", "straggler_kernel",
-                "solve_fused_kernel<resume>", "finish_kernel", "solve_track_kernel", "redecomp_kernel", "quad_kernel")
+                "solve_fused_kernel<resume>", "finish_kernel", "solve_track_kernel", "redecomp_kernel")
 
 
 def last_kernel_times():

@@ -25,7 +25,6 @@
 #include "pnpl_extract.cuh"
 #include "pnpl_solve.cuh"
 #include "pnpl_warp.cuh"
-#include "pnpl_quad.cuh"
 #include "pnpl_track.cuh"
 #include "pnpl_track2.cuh"
 
@@ -42,8 +41,8 @@ thread_local int g_launches = 0;
 
 // optional per-kernel timing of the last `solve` (desc.timing != 0): CUDA events on the
 // caller's stream between the launches.  Slots: pre, admm32, ortho, fused, straggler,
-// resume, finish, track, redecomp, quad.
-constexpr int N_TIMED = 10;
+// resume, finish, track, redecomp.
+constexpr int N_TIMED = 9;
 thread_local cudaEvent_t g_ev[N_TIMED + 1];
 thread_local bool g_ev_ready = false;
 thread_local int g_ev_slot[N_TIMED + 1];   // kernel slot that starts at event i, -1 = end
@@ -255,8 +254,7 @@ enum {
     CTRL_TRK_NEXT = 8,   // queue head of the tracked solver
     CTRL_TRK_DONE = 9,   // CTAs of the tracked solver that have finished (the concurrent service kernel stops then)
     CTRL_SVC_NEXT = 10,  // tickets (entries of fail_list) taken by the concurrent service kernel
-    CTRL_NSTRAG_START = 11,  // slab entries that exist when straggler_kernel starts (snapshot of CTRL_NSTRAG)
-    CTRL_QUAD_NEXT = 12      // queue head of quad_kernel (slab entries)
+    CTRL_NSTRAG_START = 11   // slab entries that exist when straggler_kernel starts (snapshot of CTRL_NSTRAG)
 };
 
 // RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
@@ -881,12 +879,8 @@ __device__ __forceinline__ void warp_serve_record(cvx::WarpSmem& S, const Opts& 
 // `direct_max`): the entries are taken straight from the tracked solver's hand-back list (warp_serve_record) instead
 // of going through redecomp_kernel and one pass of the thread solver first (~0.17 ms of latency for a handful of
 // problems).  Entries the concurrent service kernel has already finished are marked (fail_list < -1) / flagged.
-// With `budget` > 0 a warp lends a problem that many iterations at most; what is unfinished then (flags 0 in its slab
-// entry) is taken over by quad_kernel, four warps per problem -- and when no more than `quad_max` problems are waiting
-// here in the first place, the slab entries are left to that kernel at once (this one only decomposes the DIRECT ones).
 __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned long long* ctrl, double* slab,
-                                                            const int32_t* fail_list, const double* pre, int direct_max,
-                                                            int budget, int quad_max)
+                                                            const int32_t* fail_list, const double* pre, int direct_max)
 {
     extern __shared__ double smem[];
     cvx::WarpSmem& S = reinterpret_cast<cvx::WarpSmem*>(smem)[threadIdx.x >> 5];
@@ -897,20 +891,16 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
     // service kernel gave back unfinished), then -- DIRECT mode -- the entries of the hand-back list nobody has served
     const unsigned long long n_slab = *(volatile unsigned long long*)(ctrl + CTRL_NSTRAG_START);
     const unsigned long long n = n_slab + (direct ? n_fail : 0ULL);
-    const bool few = budget > 0 && n <= (unsigned long long)quad_max;   // quad_kernel iterates, from the start
     uint32_t pk[9];
     cvx::sweep_tables(lane, pk);
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(ctrl + CTRL_STRAG_NEXT, 1ULL);
         k = __shfl_sync(0xffffffffu, k, 0);
-        if (few) k += n_slab;   // tickets of the DIRECT entries only
         if (k >= n) break;
         if (k >= n_slab) {
             const int64_t b = fail_list[k - n_slab];
-            // (no service kernel is running any more: ~0 "warps" = never leave before the budget is spent)
-            if (b >= 0)
-                warp_serve_record(S, o, lane, pk, ctrl, pre + b * cvx::PRE_DOUBLES, b, slab, few ? 1 : budget, 0, ~0ULL);
+            if (b >= 0) warp_serve_record(S, o, lane, pk, ctrl, pre + b * cvx::PRE_DOUBLES, b, slab, 0);
             continue;
         }
         double* h = slab + k * cvx::HAND_DOUBLES;
@@ -934,7 +924,7 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
         double rho = h[cvx::HO_RHO];
         __syncwarp();
         bool converged = false;
-        cvx::warp_dr_loop(S, o, lane, it, converged, rho, (budget > 0 && it + budget < o.max_iters) ? it + budget : o.max_iters);
+        cvx::warp_dr_loop(S, o, lane, it, converged, rho, o.max_iters);
         for (int p = lane; p < 55; p += 32) {
             int r, c;
             cvx::unpack_idx(p, r, c);
@@ -946,67 +936,9 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
         if (lane == 0) {
             h[cvx::HO_IT] = (double)it;
             h[cvx::HO_RHO] = rho;
-            h[cvx::HO_FLAGS] = (converged ? 1.0 : 0.0) + ((converged || it >= o.max_iters) ? 2.0 : 0.0);
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// Quad kernel: FOUR warps (one CTA) per problem (pnpl_quad.cuh) -- the lowest-latency DR iteration, for what is
-// still unfinished in the hand-over slab after straggler_kernel: the cap runners and slowest problems of a batch, which
-// would otherwise keep a lone warp per SM busy for milliseconds.  CTAs pull slab entries from a counter.
-// ---------------------------------------------------------------------------------
-constexpr int QUAD_CTAS_PER_SM = 6;
-constexpr int QUAD_BUDGET = 200;   // iterations straggler_kernel spends on a problem before it leaves it to quad_kernel
-__global__ void __launch_bounds__(cvx::QUAD_NT, QUAD_CTAS_PER_SM) quad_kernel(Opts o, unsigned long long* ctrl, double* slab)
-{
-    __shared__ cvx::QuadSmem Q;
-    __shared__ unsigned long long s_k;
-    cvx::WarpSmem& S = Q.W;
-    const int tid = threadIdx.x;
-    const unsigned long long n = *(volatile unsigned long long*)(ctrl + CTRL_NSTRAG);   // every producer has finished
-    for (;;) {
-        if (tid == 0) s_k = atomicAdd(ctrl + CTRL_QUAD_NEXT, 1ULL);
-        __syncthreads();
-        const unsigned long long k = s_k;
-        __syncthreads();
-        if (k >= n) break;
-        double* h = slab + k * cvx::HAND_DOUBLES;
-        if (((int)h[cvx::HO_FLAGS] & 2) != 0) continue;   // the DR loop of this problem is over
-        if (tid < 100) {
-            const int r = tid / 10, c = tid - 10 * r;
-            S.M[tid] = h[cvx::HO_M + cvx::sidx(r, c)];
-            S.V[tid] = h[cvx::HO_V + tid];
-            S.Q[tid] = (r < 9 && c < 9) ? h[cvx::HO_Q + cvx::sidx(r, c)] : 0.0;
-        }
-        if (tid < 10) S.L[tid] = h[cvx::HO_L + tid];
-        if (tid < 56) {
-            S.gp[tid] = S.sp[tid] = S.gk[tid] = 0.f;
-#pragma unroll
-            for (int j = 0; j < cvx::AA_M; ++j) S.dG[j][tid] = S.dS[j][tid] = 0.f;
-        }
-        if (tid >= 64 && tid < 64 + cvx::AA_GRAM_WORDS) S.gram[tid - 64] = 0.f;
-        if (tid >= 96 && tid < 112) S.dots[tid - 96] = 0.f;
-        int it = (int)h[cvx::HO_IT];
-        double rho = h[cvx::HO_RHO];
-        bool converged = false;
-        __syncthreads();
-        cvx::quad_dr_loop(Q, o, tid, it, converged, rho, o.max_iters);
-        if (tid < 55) {
-            int r, c;
-            cvx::unpack_idx(tid, r, c);
-            h[cvx::HO_M + tid] = S.M[r * 10 + c];
-            if (r < 9) h[cvx::HO_Q + tid] = S.Q[r * 10 + c];   // Q / rho changes with a penalty rescale
-        }
-        if (tid < 100) h[cvx::HO_V + tid] = S.V[tid];
-        if (tid < 10) h[cvx::HO_L + tid] = S.L[tid];
-        if (tid == 0) {
-            h[cvx::HO_IT] = (double)it;
-            h[cvx::HO_RHO] = rho;
             h[cvx::HO_FLAGS] = (converged ? 1.0 : 0.0) + 2.0;
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -1949,17 +1881,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         mark(tm, 4, st);
         // snapshot of the slab's length: straggler_kernel allocates further entries while it runs
         cudaMemcpyAsync(ctrl + CTRL_NSTRAG_START, ctrl + CTRL_NSTRAG, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st);
-        // a warp lends a problem QUAD_BUDGET iterations; the rest is for four warps per problem (quad_kernel), and so is
-        // everything when no more problems are waiting than that kernel runs at once
-        static const int quad_budget = getenv("CVXPNPL_B200_QUAD_BUDGET") ? atoi(getenv("CVXPNPL_B200_QUAD_BUDGET")) : QUAD_BUDGET;
-        const int quad_max = (int)(n_sm * QUAD_CTAS_PER_SM);
         straggler_kernel<<<(unsigned)wblocks, NT_W, SMEM_W_BYTES, st>>>(o, ctrl, slab, tracked ? fail_list : nullptr, pre,
-                                                                        direct_max, quad_budget, quad_max);
-        if (quad_budget > 0) {
-            mark(tm, 9, st);
-            quad_kernel<<<(unsigned)quad_max, cvx::QUAD_NT, 0, st>>>(o, ctrl, slab);
-            ++g_launches;
-        }
+                                                                        direct_max);
         mark(tm, 5, st);
         solve_fused_kernel<true><<<(unsigned)blocks, NT, SMEM_BYTES, st>>>(dd, o, ctrl, pre, park, slab, nullptr, nullptr,
                                                                           -1, 0, slots, 0);
@@ -1985,7 +1908,7 @@ int cvxpnpl_b200_prepass(const cvxpnpl_b200_desc* d, int64_t first, int64_t coun
 
 int cvxpnpl_b200_kernel_times(float* ms, int n)
 {
-    if (!ms || n < 9) return fail(-5, "kernel_times needs room for at least 9 floats");
+    if (!ms || n < N_TIMED) return fail(-5, "kernel_times needs room for 9 floats");
     for (int i = 0; i < n; ++i) ms[i] = 0.f;
     if (g_ev_n < 2) return fail(-9, "the last solve on this thread was not timed (desc.timing = 0)");
     cudaError_t e = cudaEventSynchronize(g_ev[g_ev_n - 1]);
@@ -1994,7 +1917,7 @@ int cvxpnpl_b200_kernel_times(float* ms, int n)
         float t = 0.f;
         e = cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]);
         if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-        if (g_ev_slot[i] >= 0 && g_ev_slot[i] < n) ms[g_ev_slot[i]] = t;
+        if (g_ev_slot[i] >= 0) ms[g_ev_slot[i]] = t;
     }
     return 0;
 }

@@ -123,8 +123,7 @@ int cvxpnpl_b200_prepass(const cvxpnpl_b200_desc* desc, int64_t first, int64_t c
 
 /* Device time of each kernel of the last `solve` issued by this host thread with
  * desc.timing != 0, in ms: pre, admm32, ortho, solve_fused, straggler, resume, finish, solve_track,
- * redecomp, quad (n >= 9, the tenth is filled when n >= 10; 0 for kernels that were not launched).  Synchronises on
- * the last event. */
+ * redecomp (n >= 9; 0 for kernels that were not launched).  Synchronises on the last event. */
 int cvxpnpl_b200_kernel_times(float* ms, int n);
 
 /* Stage: correspondences -> Q [B,9,9] (= A'A of cvxpnpl.py:475) and Bmat [B,3,9]

@@ -806,7 +806,7 @@ def test_two_devices_one_process(cb):
     assert float((outs[0].R[:, 0].cpu() - outs[1].R[:, 0].cpu()).abs().max()) < 1e-8
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker_all(rank, world, port, q):
     import os
     import sys
     sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
@@ -833,7 +833,7 @@ def _nccl_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_solve_sharded_nccl(cb):
+def test_solve_sharded_nccl_all_gpus(cb):
     """cvxpnpl_b200.distributed.solve_sharded over NCCL: the batch sharded by contiguous ranges over every GPU of
     the box (one process per GPU), rows all-gathered in place, result equal to the single-GPU solve.  On a
     one-GPU box this still runs the NCCL path with world size 1."""
@@ -845,7 +845,7 @@ def test_solve_sharded_nccl(cb):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker_all, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
