@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sides", action="store_true", help="skip the side_configs block")
+    ap.add_argument("--e2e-parts", type=int, default=3, help="sub-batches of the end-to-end step (HostStager(parts=...))")
     ap.add_argument("--admm", default="f64", choices=["f64", "f32"],
                     help="f64: FP64 ADMM throughout (the headline, BASELINE.json configs[2]); f32: FP32 first "
                          "phase + FP64 tail and extraction (configs[3]), a side measurement")
@@ -403,10 +404,20 @@ def run_ours(a):
     # the next ones; then the solve (the finish kernel packs the records), the all-gather and the D2H read
     stager = cb.HostStager(K, dev, chunks=4, admm_dtype=a.admm)
 
-    def step_e2e():
+    def step_e2e_one():
         o = stager.solve(host, record=gat.local)
         gat.gather()
         host_out.copy_(gat.local, non_blocking=True)
+        return o
+
+    # ... and the same entry point with parts=N: the batch as N independent sub-batch solves on their own streams;
+    # sub-batch p starts when its slice has arrived and its rows go back to the host under the kernels of the next
+    # ones (HostStager docstring).  Same bytes up and down inside the timed region; this is the e2e headline.
+    stager_p = cb.HostStager(K, dev, parts=a.e2e_parts, admm_dtype=a.admm)
+
+    def step_e2e():
+        o = stager_p.solve(host, record=gat.local, host_record=host_out)
+        gat.gather()
         return o
 
     def timed(fn, steps, warmup, marks=None):
@@ -499,6 +510,9 @@ def run_ours(a):
     ms_2if = two_in_flight_ms(cb, torch, dev, K, devin, B, a.admm, 2 * a.steps, a.warmup, flush) if world == 1 else None
 
     ms_e2e = timed(step_e2e, a.steps, a.warmup)
+    torch.cuda.synchronize()
+    e2e_rows_ok = bool(torch.equal(torch.nan_to_num(host_out), torch.nan_to_num(gat.local.cpu())))
+    ms_e2e_one = timed(step_e2e_one, a.steps, a.warmup)
 
     # streaming variant (extra, not the e2e headline): cvxpnpl_b200.HostPipeline double-buffers the
     # inputs, so the H2D copy of step k+1 runs on a copy stream during the solve of step k.  Every
@@ -568,7 +582,16 @@ def run_ours(a):
                        "collective": "in-place all_gather of [B,15] pose records (NCCL)" if world > 1 else "none",
                        "host_affinity": numa},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / a.steps},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "what": f"cvxpnpl_b200.HostStager(parts={a.e2e_parts}).solve(host tensors, host_record=...): pinned host "
+                            "correspondences in, pinned host [B,15] pose rows out, the batch as independent sub-batch "
+                            "solves on their own streams (copies of later sub-batches and rows of earlier ones under "
+                            "the kernels)",
+                    "host_rows_equal_device_rows": e2e_rows_ok},
+            "e2e_one_solve": {"what": "same bytes through HostStager(parts=1): ONE solve whose pre-pass runs slice by "
+                                      "slice under the copies; the solver waits for the last byte, the rows leave after "
+                                      "the last problem (the round-1 / r2a-r2bh e2e path)",
+                              "value": total / (ms_e2e_one * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_one / a.steps},
             "e2e_pipelined": {"what": "same as e2e but through cvxpnpl_b200.HostPipeline: the H2D copy of the next "
                                       "batch overlaps the solve of the current one (copy stream); extra, not the headline",
                               "value": total / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe / a.steps},

@@ -1069,6 +1069,22 @@ __global__ void __launch_bounds__(NT_P) pre_kernel(cvxpnpl_b200_desc d, Opts o, 
     }
 }
 
+// The early iterations as a kernel of their own (track_early on the record pre_kernel<false> left): assembly and start
+// decomposition need 100 doubles of shared memory per thread and run with eight warps per SM, the early iterations
+// need 221 and run with four -- in one kernel (pre_kernel<true>) everything runs with four.
+__global__ void __launch_bounds__(NT_P) early_kernel(Opts o, double* pre, int64_t first, int64_t last)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t b = first + (int64_t)blockIdx.x * NT_P + tid;
+    if (b >= last) return;
+    cvx::Arr<NT_P> V{smem + tid};
+    cvx::Arr<NT_P> M{smem + (size_t)100 * NT_P + tid};
+    cvx::Arr<NT_P> T{smem + (size_t)155 * NT_P + tid};
+    cvx::Arr<NT_P> L{smem + (size_t)211 * NT_P + tid};
+    cvx::track_early(pre + b * cvx::PRE_DOUBLES, o, V, M, T, L);
+}
+
 // counting sort of the buckets -> queue order (likely stragglers first)
 __global__ void bucket_scan_kernel(const unsigned* count, unsigned* offset)
 {
@@ -1723,6 +1739,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(pre_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PE_BYTES);
             if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(early_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PE_BYTES);
+            if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(solve_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_TRK_BYTES);
             if (e == cudaSuccess)
@@ -1779,18 +1797,24 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     unsigned* bucket_count = (unsigned*)(ctrl + 16);
     unsigned* bucket_offset = bucket_count + N_BUCKETS;
     mark(tm, 0, st);
+    int n_pre_launches = 1;
     if (mode != 2) {
         const int64_t lo = mode == 1 ? first : 0, hi = mode == 1 ? first + count : d->batch;
         if (hi > lo) {
-            if (early)
-                pre_kernel<true><<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_PE_BYTES, st>>>(
-                    dd, o, pre, bucket_count, bucket_of, lo, hi);
-            else
-                pre_kernel<false><<<(unsigned)((hi - lo + NT_P - 1) / NT_P), NT_P, SMEM_P_BYTES, st>>>(
-                    dd, o, pre, bucket_count, bucket_of, lo, hi);
+            static const bool fused_pre = getenv("CVXPNPL_B200_FUSED_PRE") != nullptr;   // (A/B: one kernel)
+            const unsigned nb = (unsigned)((hi - lo + NT_P - 1) / NT_P);
+            if (early && fused_pre) {
+                pre_kernel<true><<<nb, NT_P, SMEM_PE_BYTES, st>>>(dd, o, pre, bucket_count, bucket_of, lo, hi);
+            } else {
+                pre_kernel<false><<<nb, NT_P, SMEM_P_BYTES, st>>>(dd, o, pre, bucket_count, bucket_of, lo, hi);
+                if (early) {
+                    early_kernel<<<nb, NT_P, SMEM_PE_BYTES, st>>>(o, pre, lo, hi);
+                    ++n_pre_launches;
+                }
+            }
         }
         if (mode == 1) {
-            g_launches = 1;
+            g_launches = n_pre_launches;
             cudaError_t e1 = cudaGetLastError();
             if (e1 != cudaSuccess) return fail((int)e1, cudaGetErrorString(e1));
             return 0;
@@ -1798,7 +1822,7 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     }
     bucket_scan_kernel<<<1, 32, 0, st>>>(bucket_count, bucket_offset);
     bucket_scatter_kernel<<<(unsigned)((d->batch + 255) / 256), 256, 0, st>>>(d->batch, bucket_of, bucket_offset, order);
-    g_launches = (mode == 2) ? 4 : 5;   // pre-pass, two sort kernels, solver, finish
+    g_launches = (mode == 2) ? 4 : 4 + n_pre_launches;   // pre-pass, two sort kernels, solver, finish
     const double* warm_in = nullptr;
     if (d->fp32_iters > 0) {
         // FP32 first phase, then its bases made orthonormal in FP64

@@ -82,33 +82,123 @@ class HostPipeline:
 
 
 class HostStager:
-    """One batch from pinned HOST memory with the copy hidden as far as a single step allows:
-    the correspondences go up in `chunks` slices on a copy stream and the pre-pass kernel
-    (assembly + start decomposition, `cvxpnpl_b200_prepass`) of each slice runs as soon as
-    that slice has landed, i.e. under the copies of the following slices.  Everything after
-    the pre-pass needs the whole batch and follows on the current stream."""
+    """One batch from pinned HOST memory with the copy hidden as far as a single step allows.
 
-    def __init__(self, K, device, chunks=4, **solve_kwargs):
+    parts == 1: the correspondences go up in `chunks` slices on a copy stream and the pre-pass
+    kernels (assembly + start decomposition + early iterations, `cvxpnpl_b200_prepass`) of each
+    slice run as soon as that slice has landed, i.e. under the copies of the following slices.
+    Everything after the pre-pass needs the whole batch and follows on the current stream: the
+    solver only starts when the last byte has arrived (64 MB, ~1.3 ms for 1e5 PnPL problems),
+    and the record only leaves when the last problem is done.
+
+    parts > 1: the problems are independent, so the batch is solved as `parts` contiguous
+    sub-batches, each a complete solve on a stream of its own with its own workspace: sub-batch
+    p starts when ITS slice has arrived, the slices of the later ones arrive under its kernels,
+    and its `[n, 15]` rows go back to the host (`host_record`) under the kernels of the next
+    ones.  Persistent kernels of consecutive sub-batches hand the SMs over CTA by CTA, so the
+    GPU stays as busy as with one solve; only the first slice's copy and the last sub-batch's
+    rows are outside the compute."""
+
+    # problems in the LAST slice: its pre-pass is the only one that is not hidden behind a copy, and the pre-pass
+    # kernels need the same time for anything up to one wave (148 SMs x 2 CTAs x 64 problems)
+    LAST_SLICE = 12288
+
+    def __init__(self, K, device, chunks=4, parts=1, **solve_kwargs):
         self.device = torch.device(device)
         self.K = torch.as_tensor(K, dtype=torch.float64).to(self.device)
         self.chunks = int(chunks)
+        self.parts = max(1, int(parts))
         self.kw = solve_kwargs
         self.copy_stream = torch.cuda.Stream(self.device)
         self.buf = None
         self.ws = None
         self.out = None
         self.done = None     # event: the previous solve no longer reads the input buffers
+        self.part_streams = None
+        self.part_ws = None
+        self.part_out = None
 
-    def solve(self, host: Dict[str, torch.Tensor], record=None) -> BatchedPoses:
-        """`record`: optional [B,15] CUDA tensor for the packed rows (see solve_batched)."""
+    def _solve_parts(self, host, B, record, host_record) -> BatchedPoses:
+        dev, P = self.device, self.parts
+        bounds = [(p * B) // P for p in range(P + 1)]
+        if self.buf is None or self.buf.keys() != host.keys() or any(self.buf[k].shape != v.shape for k, v in host.items()):
+            self.buf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+            self.part_ws = self.part_out = None
+        if self.part_streams is None:
+            self.part_streams = [torch.cuda.Stream(dev) for _ in range(P)]
+        if self.part_ws is None:
+            self.part_ws = [Workspace(hi - lo, dev) for lo, hi in zip(bounds[:-1], bounds[1:])]
+            with torch.cuda.device(dev):
+                self.out = BatchedPoses(
+                    R=torch.empty((B, 4, 3, 3), dtype=torch.float64, device=dev),
+                    t=torch.empty((B, 4, 3), dtype=torch.float64, device=dev),
+                    n_poses=torch.empty(B, dtype=torch.int32, device=dev),
+                    status=torch.empty(B, dtype=torch.int32, device=dev),
+                    iters=torch.empty(B, dtype=torch.int32, device=dev),
+                    obj=torch.empty((B, 2), dtype=torch.float64, device=dev))
+                self.own_record = torch.empty((B, RECORD), dtype=torch.float64, device=dev)
+            o = self.out
+            self.part_out = [BatchedPoses(R=o.R[lo:hi], t=o.t[lo:hi], n_poses=o.n_poses[lo:hi], status=o.status[lo:hi],
+                                          iters=o.iters[lo:hi], obj=o.obj[lo:hi]) for lo, hi in zip(bounds[:-1], bounds[1:])]
+        if record is None:
+            record = self.own_record
+        main = torch.cuda.current_stream(dev)
+        entry = torch.cuda.Event()
+        entry.record(main)
+        events = []
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(entry)
+            if self.done is not None:
+                self.copy_stream.wait_event(self.done)
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                for k, v in host.items():
+                    self.buf[k][lo:hi].copy_(v[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                events.append(ev)
+        launches = 0
+        for p, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+            if hi <= lo:
+                continue
+            sp = self.part_streams[p]
+            with torch.cuda.stream(sp):
+                sp.wait_event(entry)
+                sp.wait_event(events[p])
+                sub = {k: v[lo:hi] for k, v in self.buf.items()}
+                po = solve_batched(self.K, pts_2d=sub.get("pts_2d"), pts_3d=sub.get("pts_3d"), line_2d=sub.get("line_2d"),
+                                   line_3d=sub.get("line_3d"), workspace=self.part_ws[p], out=self.part_out[p],
+                                   record=record[lo:hi], **self.kw)
+                launches += po.launches
+                if host_record is not None:
+                    host_record[lo:hi].copy_(record[lo:hi], non_blocking=True)   # under the kernels of the next parts
+            main.wait_stream(sp)
+        self.out.launches = launches
+        self.out.record = record
+        self.done = torch.cuda.Event()
+        self.done.record(main)
+        return self.out
+
+    def solve(self, host: Dict[str, torch.Tensor], record=None, host_record=None) -> BatchedPoses:
+        """`record`: optional [B,15] CUDA tensor for the packed rows (see solve_batched); `host_record`: optional
+        pinned [B,15] host tensor that receives those rows (valid after a synchronisation of the current stream)."""
         host = {k: v for k, v in host.items() if v is not None and v.shape[1] > 0}
         B = next(iter(host.values())).shape[0]
-        if self.buf is None or self.buf.keys() != host.keys() or any(self.buf[k].shape != v.shape for k, v in host.items()):
+        if self.parts > 1 and B >= self.parts * 4096:
+            return self._solve_parts(host, B, record, host_record)
+        if (self.buf is None or self.ws is None or self.buf.keys() != host.keys()
+                or any(self.buf[k].shape != v.shape for k, v in host.items())):
             self.buf = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
             with torch.cuda.device(self.device):       # the workspace is sized for THIS device's SM count
                 self.ws, self.out = Workspace(B, self.device), None
+            self.part_ws = self.part_out = None
+        if host_record is not None and record is None:
+            record = torch.empty((B, RECORD), dtype=torch.float64, device=self.device)
         main = torch.cuda.current_stream(self.device)
-        bounds = [(c * B) // self.chunks for c in range(self.chunks + 1)]
+        if self.chunks > 1 and B > self.chunks * self.LAST_SLICE:
+            head = B - self.LAST_SLICE          # equal slices, then a short last one
+            bounds = [(c * head) // (self.chunks - 1) for c in range(self.chunks)] + [B]
+        else:
+            bounds = [(c * B) // self.chunks for c in range(self.chunks + 1)]
         events = []
         entry = torch.cuda.Event()
         entry.record(main)       # the copies start after everything already queued on the caller's stream
@@ -129,12 +219,14 @@ class HostStager:
                 main.wait_event(ev)
                 if hi > lo:
                     _lib.check(lib.cvxpnpl_b200_prepass(ctypes.byref(d), lo, hi - lo, ctypes.c_void_p(stream)))
-                    n += 1
+                    n += int(lib.cvxpnpl_b200_last_launch_count())
             return n
 
         self.out = solve_batched(self.K, pts_2d=self.buf.get("pts_2d"), pts_3d=self.buf.get("pts_3d"),
                                  line_2d=self.buf.get("line_2d"), line_3d=self.buf.get("line_3d"), workspace=self.ws,
                                  out=self.out, _prepass_hook=hook, record=record, **self.kw)
+        if host_record is not None:
+            host_record.copy_(record, non_blocking=True)
         self.done = torch.cuda.Event()
         self.done.record(main)
         return self.out

@@ -556,7 +556,7 @@ def test_fp32_admm_matches_oracle(cb, n_pts, n_lines):
     d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=91)
     m = _solve(cb, d, n_pts, n_lines, admm_dtype="f32")
     a = _solve(cb, d, n_pts, n_lines)
-    assert m.launches == a.launches + 2     # admm32_kernel + ortho_kernel really ran
+    assert m.launches == a.launches + 1     # admm32_kernel + ortho_kernel really ran (and no early_kernel before them)
     sm, sa = (m.status & 0xFF).cpu().numpy(), (a.status & 0xFF).cpu().numpy()
     ok = (sm == 0) & (sa == 0) & (m.n_poses.cpu().numpy() == 1) & (a.n_poses.cpu().numpy() == 1)
     assert ok.mean() > 0.95
@@ -576,12 +576,12 @@ def test_fp32_admm_matches_oracle(cb, n_pts, n_lines):
 
 def test_kernel_times_and_launch_count(cb):
     """cvxpnpl_b200_kernel_times: CUDA-event time of every kernel of a timed solve; the
-    ten (twelve with the FP32 first phase) launches of the tracked path -- nine on the caller's stream and the
-    concurrent service kernel on the library's side stream -- are all there and add up to the step; the
-    full-decomposition path (psd="full") has seven."""
+    eleven (twelve with the FP32 first phase, which has no early iterations) launches of the tracked path -- ten on the
+    caller's stream and the concurrent service kernel on the library's side stream -- are all there and add up to the
+    step; the full-decomposition path (psd="full") has seven."""
     from cvxpnpl_b200 import synth
     d = synth.make_batch(20000, 8, 4, noise=1.0, seed=5)
-    for admm, n_launch, extra in (("f64", 10, ()), ("f32", 12, ("admm32_kernel", "ortho_kernel"))):
+    for admm, n_launch, extra in (("f64", 11, ()), ("f32", 12, ("admm32_kernel", "ortho_kernel"))):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _solve(cb, d, 8, 4, admm_dtype=admm)        # warm-up
         s.record()
@@ -614,8 +614,9 @@ def test_tracked_psd_matches_full_decomposition(cb, n_pts, n_lines, B, psd):
     d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=1234)
     a = _solve(cb, d, n_pts, n_lines, psd="full")
     w = _solve(cb, d, n_pts, n_lines, psd=psd)
-    # solve_track_kernel + redecomp_kernel (+ the concurrent service kernel beside the two-thread solver) really ran
-    assert w.launches == a.launches + (3 if psd == "track" else 2)
+    # early_kernel + solve_track_kernel + redecomp_kernel (+ the concurrent service kernel beside the two-thread solver)
+    # really ran
+    assert w.launches == a.launches + (4 if psd == "track" else 3)
     sa, sw = (a.status & 0xFF).cpu().numpy(), (w.status & 0xFF).cpu().numpy()
     na, nw = a.n_poses.cpu().numpy(), w.n_poses.cpu().numpy()
     well_posed = n_pts + n_lines >= 8
@@ -669,7 +670,36 @@ def test_host_stager_matches_direct_solve(cb):
         assert float((res.R[:, 0] - ref.R[:, 0]).abs().cpu()[ok].max()) < 1e-7
         assert float((res.t[:, 0] - ref.t[:, 0]).abs().cpu()[ok].max()) < 1e-7
         n_slices = len({(c * B) // 4 for c in range(5)}) - 1     # non-empty slices
-        assert res.launches == ref.launches + n_slices - 1        # one pre-pass launch per slice instead of one
+        n_pre = 2 if B > 2368 else 1                              # pre-pass kernels of the tracked solver: two
+        assert res.launches == ref.launches + (n_slices - 1) * n_pre   # the pre-pass once per slice instead of once
+
+
+def test_host_stager_parts_matches_direct_solve(cb):
+    """HostStager(parts=3): the batch as three independent sub-batch solves on their own streams (sub-batch p starts
+    when its slice has arrived; its rows go back to the host under the kernels of the next ones) -- same poses as a
+    direct solve, rows in the pinned host record equal to the device fields."""
+    from cvxpnpl_b200 import synth
+    n_pts, n_lines, B = 8, 4, 30001
+    d = synth.make_batch(B, n_pts, n_lines, noise=1.0, seed=322)
+    host = {k: torch.from_numpy(d[k]).pin_memory() for k in ("pts_2d", "pts_3d", "line_2d", "line_3d")}
+    stager = cb.HostStager(d["K"], "cuda:0", parts=3)
+    host_rec = torch.empty((B, 15), dtype=torch.float64).pin_memory()
+    for _ in range(2):                           # second call reuses buffers, streams and workspaces
+        host_rec.fill_(-7.0)
+        res = stager.solve(host, host_record=host_rec)
+        torch.cuda.synchronize()
+    ref = _solve(cb, d, n_pts, n_lines)
+    assert ((res.status & 0xFF) == 0).all() and ((ref.status & 0xFF) == 0).all()
+    assert float((res.R[:, 0] - ref.R[:, 0]).abs().max()) < 1e-7
+    assert float((res.t[:, 0] - ref.t[:, 0]).abs().max()) < 1e-7
+    assert torch.equal(host_rec[:, :9], res.R[:, 0].reshape(B, 9).cpu())
+    assert torch.equal(host_rec[:, 9:12], res.t[:, 0].cpu())
+    assert torch.equal(host_rec[:, 14].to(torch.int32), res.iters.cpu())
+    # a batch too small to split goes through the single-solve path of the same object
+    small = {k: v[:100] for k, v in host.items()}
+    r2 = stager.solve(small)
+    torch.cuda.synchronize()
+    assert float((r2.R[:, 0] - ref.R[:100, 0]).abs().max()) < 1e-7
 
 
 def test_record_output_matches_fields(cb):
