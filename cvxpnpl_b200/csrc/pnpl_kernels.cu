@@ -516,10 +516,12 @@ solve_track_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, double
 // ---------------------------------------------------------------------------------
 // Tracked persistent solver, TWO threads per problem (pnpl_track2.cuh): 256 threads per CTA, still 128 problems per
 // SM; thread p of warps 0-3 (role A) and thread p of warps 4-7 (role B) own problem slot p together.  Warp w and
-// warp w + 4 address the same tensor-memory lanes (role A uses columns 0-255, role B 256-511 of each lane); all eight
-// warps meet at a CTA barrier between the phases of a pass (the barrier a pair needs, widened to the CTA so that the
-// four warps of a role stay in lock-step and share the instruction-cache lines of the role's code).  Role A owns the queue, the hand-over
-// decision, parking and hand-back; role B follows through a control word in shared memory.
+// warp w + 4 address the same tensor-memory lanes (role A uses columns 0-255, role B 256-511 of each lane).  Between
+// the phases of a pass the two warps of a pair meet at a named barrier of their own (64 threads); all eight warps
+// meet ONCE per pass, at the vote at the top of the loop, which is enough to keep them on the same instruction-cache
+// lines now that both roles run the same code (with CTA-wide barriers between all phases -- the r2o..r2bm form --
+// every barrier waits for the slowest of the four pairs: 19 % of the stall samples).  Role A owns the queue, the
+// hand-over decision, parking and hand-back; role B follows through a control word in shared memory.
 // Shared memory per problem: the 178 doubles of solve_track_kernel + 5 doubles and 22 floats of exchange scratch.
 // ---------------------------------------------------------------------------------
 constexpr int NT2 = 2 * NT;
@@ -530,6 +532,7 @@ constexpr size_t SMEM_TRK2_BYTES = (size_t)NT * TRK2_SMEM_DOUBLES * sizeof(doubl
 
 // CTA-wide barrier / votes from the two role-specific code paths: named barrier 1 with an explicit thread count (the
 // hardware counts arrivals, whatever instruction they come from)
+#ifdef CVX_CTA_BARRIERS
 struct CtaSync {
     __device__ __forceinline__ void operator()() const { asm volatile("barrier.cta.sync 1, %0;" ::"n"(2 * NT) : "memory"); }
 };
@@ -540,6 +543,22 @@ struct CtaVote {
         asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; barrier.cta.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
                      : "=r"(r) : "r"((uint32_t)f), "n"(2 * NT) : "memory");
         return r != 0;
+    }
+};
+#endif
+// The same for ONE pair of warps (w, w + 4): named barriers 2..5, 64 threads.  The eight warps then meet only once per
+// pass (cta_vote_and at the top of the loop), which is what keeps them on the same instruction-cache lines.
+struct PairSync {
+    int id;
+    __device__ __forceinline__ void operator()() const { asm volatile("barrier.cta.sync %0, 64;" ::"r"(id) : "memory"); }
+};
+struct PairVote {
+    int id;
+    __device__ __forceinline__ bool operator()(bool f) const
+    {
+        // both warps of a pair hold the same flags lane by lane, so the OR over one warp is the OR over the pair
+        asm volatile("barrier.cta.sync %0, 64;" ::"r"(id) : "memory");
+        return __any_sync(0xffffffffu, f) != 0;
     }
 };
 __device__ __forceinline__ bool cta_vote_and(bool f)
@@ -571,8 +590,15 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
     cvx::Arr<NT> X{smem + (size_t)TRK2_X * NT + p};
     cvx::ArrT<NT, float> XF{reinterpret_cast<float*>(smem + (size_t)TRK2_XF * NT) + p};
     const HistTmem H{tmem_base + ((uint32_t)wq << 21)};
+    // barriers of a pass: per warp pair (measured: solver kernel 3.885 -> 3.65 ms against CTA-wide ones, which cost
+    // 19 % of the stall samples -- every barrier waited for the slowest of four pairs); -DCVX_CTA_BARRIERS for A/B
+#ifdef CVX_CTA_BARRIERS
     const CtaSync sync;
     const CtaVote vote;
+#else
+    const PairSync sync{2 + wq};
+    const PairVote vote{2 + wq};
+#endif
     {
         uint32_t zero[32];
 #pragma unroll
