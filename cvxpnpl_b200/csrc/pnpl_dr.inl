@@ -60,6 +60,61 @@ CVX_HD void jacobi_cs(CVX_REAL app, CVX_REAL aqq, CVX_REAL apq, CVX_REAL& c, CVX
 template <int S>
 CVX_HD CVX_REAL jacobi_sweep_reg(CVX_REAL t[55], ArrT<S, CVX_REAL> V)
 {
+#if defined(CVX_STALE_ANGLES) && !defined(__CUDA_ARCH__)
+    // EXPERIMENT (host build only): all 45 rotation angles from the matrix as it is at the START of the sweep, then
+    // the nine rounds applied without recomputing them -- the nine dependent angle chains of a sweep become one.
+    {
+        CVX_REAL t0[55], off0 = CVX_REAL(0.0);
+        for (int e = 0; e < 55; ++e) t0[e] = t[e];
+        int perm[10];
+        for (int i = 0; i < 10; ++i) perm[i] = i;
+        for (int round = 0; round < 9; ++round) {
+            CVX_REAL cs[5], sn[5], tn[5];
+            for (int k = 0; k < 5; ++k) {
+                const int p = jp_p(k), q = jp_q(k);
+                const int op = perm[p], oq = perm[q];
+                const CVX_REAL apq0 = t0[op > oq ? sidx(op, oq) : sidx(oq, op)];
+                off0 = fma(apq0, apq0, off0);
+                jacobi_cs(t0[sidx(op, op)], t0[sidx(oq, oq)], apq0, cs[k], sn[k], tn[k]);
+            }
+            for (int k = 0; k < 5; ++k) {
+                const int p = jp_p(k), q = jp_q(k);
+                const CVX_REAL c = cs[k], s = sn[k];
+                const CVX_REAL app = t[sidx(p, p)], aqq = t[sidx(q, q)], apq = t[sidx(q, p)];
+                t[sidx(p, p)] = c * c * app - 2 * c * s * apq + s * s * aqq;
+                t[sidx(q, q)] = s * s * app + 2 * c * s * apq + c * c * aqq;
+                t[sidx(q, p)] = c * s * (app - aqq) + (c * c - s * s) * apq;
+                for (int m = 0; m < 10; ++m) {
+                    if (m == p || m == q) continue;
+                    const CVX_REAL amp = t[sidx(m, p)], amq = t[sidx(m, q)];
+                    t[sidx(m, p)] = fma(c, amp, -s * amq);
+                    t[sidx(m, q)] = fma(s, amp, c * amq);
+                }
+            }
+            {
+                CVX_REAL u[55];
+                int np[10];
+                for (int i = 0; i < 10; ++i)
+                    for (int j = 0; j <= i; ++j) u[sidx(jp_sigma(i), jp_sigma(j))] = t[sidx(i, j)];
+                for (int e = 0; e < 55; ++e) t[e] = u[e];
+                for (int i = 0; i < 10; ++i) np[jp_sigma(i)] = perm[i];
+                for (int i = 0; i < 10; ++i) perm[i] = np[i];
+            }
+            for (int row = 0; row < 10; ++row) {
+                CVX_REAL v[10];
+                for (int j = 0; j < 10; ++j) v[j] = V[row * 10 + j];
+                for (int k = 0; k < 5; ++k) {
+                    const int p = jp_p(k), q = jp_q(k);
+                    const CVX_REAL vp = v[p], vq = v[q];
+                    v[p] = fma(cs[k], vp, -sn[k] * vq);
+                    v[q] = fma(sn[k], vp, cs[k] * vq);
+                }
+                for (int j = 0; j < 10; ++j) V[row * 10 + jp_sigma(j)] = v[j];
+            }
+        }
+        return off0;
+    }
+#endif
     CVX_REAL off = CVX_REAL(0.0);
 #pragma unroll 1
     for (int round = 0; round < 9; ++round) {

@@ -91,6 +91,7 @@ __constant__ signed char c_triples[15][10] = {CVX_TRIPLES(CVX_TRI_ROW)};
 struct WarpSmem {
     double M[100], V[100], T[100], X[100], Z[100], Q[100];   // full 10x10, row-major
     double L[10], cs[10];
+    double csall[90];   // (c, s) of the 45 pivot pairs of a sweep in round order (warp_sweep_stale)
     float gp[56], sp[56], gk[56];
     float dG[AA_M][56], dS[AA_M][56];
     float gram[AA_GRAM_WORDS], dots[16];
@@ -195,6 +196,79 @@ __device__ __forceinline__ void warp_sweep(WarpSmem& S, int lane, const uint32_t
         }
         __syncwarp();
     }
+}
+
+// The sweep of a DR iteration (warm start: T = V'MV is nearly diagonal) with all 45 rotation angles taken from T AS IT IS
+// when the sweep begins, instead of from the partly rotated matrix round by round.  The rotations are still exact
+// (orthogonal to double precision) and applied in the cyclic order, so V stays orthonormal; only the annihilation of
+// the pivots is first-order instead of exact: the off-diagonal part left behind is O(off^2 / gap), the same order a
+// cyclic sweep leaves, and the next iteration recomputes T from scratch anyway.  Measured on the host build (the same
+// change in jacobi_sweep_reg, 300..3000 problems per family, tools/stale_angles_host.py): mean DR iterations PnPL 8+4
+// 52.8 -> 52.6, PnL-6 67.5 -> 68.1, PnP-8 53.8 -> 53.8, 4 points 121.4 -> 121.3, same poses (1e-9 rad), same problems at
+// the cap.  What it buys: the nine DEPENDENT rounds of (angle chain ~270 cycles + 2x2 block update + two warp barriers,
+// ~690 cycles each: half of the warp's iteration, profiles/r2bf) become one round of angles for all pairs on 32 + 13
+// lanes, nine rounds of plain row rotations of V, and the eigenvalues as diag(V' M V) from one product -- T itself
+// is not rotated at all.
+// On entry S.T = V' M V (full form); on exit S.V is rotated and S.L holds the new eigenvalue estimates; S.X is scratch.
+__device__ __forceinline__ void warp_sweep_stale(WarpSmem& S, int lane, const uint32_t pk[9])
+{
+    // ---- angles: pivot pair number i = 5 * round + k, lanes take i = lane and i = lane + 32 ----------------------------
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i < 45) {
+            int p, q;
+            round_pair(i / 5, i % 5, p, q);
+            double c, s;
+            jacobi_cs_fast(S.T[p * 11], S.T[q * 11], S.T[q * 10 + p], c, s);
+            S.csall[2 * i] = c;
+            S.csall[2 * i + 1] = s;
+        }
+    }
+    __syncwarp();
+    // ---- nine rounds of row rotations of V: items (row lane / 5, pair lane % 5) and (row (lane + 32) / 5, pair (lane + 32) % 5)
+    const int kb = lane % 5, k1 = (lane + 32) % 5;
+    const int i0 = lane / 5, i1 = (lane + 32) / 5;
+#pragma unroll 1
+    for (int round = 0; round < 9; ++round) {
+        const int pb = (pk[round] >> 8) & 15, qb = (pk[round] >> 12) & 15, p1 = (pk[round] >> 16) & 15,
+                  q1 = (pk[round] >> 20) & 15;
+        {
+            const double c = S.csall[10 * round + 2 * kb], s = S.csall[10 * round + 2 * kb + 1];
+            const double vp = S.V[i0 * 10 + pb], vq = S.V[i0 * 10 + qb];
+            S.V[i0 * 10 + pb] = fma(c, vp, -s * vq);
+            S.V[i0 * 10 + qb] = fma(s, vp, c * vq);
+        }
+        if (lane < 18) {
+            const double c = S.csall[10 * round + 2 * k1], s = S.csall[10 * round + 2 * k1 + 1];
+            const double vp = S.V[i1 * 10 + p1], vq = S.V[i1 * 10 + q1];
+            S.V[i1 * 10 + p1] = fma(c, vp, -s * vq);
+            S.V[i1 * 10 + q1] = fma(s, vp, c * vq);
+        }
+        __syncwarp();
+    }
+    // ---- eigenvalue estimates: lambda_j = v_j' M v_j  (X = M V, then ten column dot products) --------------------------
+    for (int e = lane; e < 100; e += 32) {
+        const int r = e / 10, c = e - 10 * r;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) {
+            s0 = fma(S.M[r * 10 + k], S.V[k * 10 + c], s0);
+            s1 = fma(S.M[r * 10 + k + 1], S.V[(k + 1) * 10 + c], s1);
+        }
+        S.X[e] = s0 + s1;
+    }
+    __syncwarp();
+    if (lane < 10) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) {
+            s0 = fma(S.V[k * 10 + lane], S.X[k * 10 + lane], s0);
+            s1 = fma(S.V[(k + 1) * 10 + lane], S.X[(k + 1) * 10 + lane], s1);
+        }
+        S.L[lane] = s0 + s1;
+    }
+    __syncwarp();
 }
 
 // Cold eigen-decomposition of S.M (full form) by one warp: V = I, T = M, cyclic sweeps.  The rotations annihilate a
@@ -507,10 +581,14 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
             S.T[c * 10 + r] = s;
         }
         __syncwarp();
-        // ---- 6. one Jacobi sweep (warp_sweep) ----------------------------------------------------
+        // ---- 6. one Jacobi sweep: angles from T as it is (warp_sweep_stale); -DCVX_WARP_EXACT_SWEEP: round by round -------
+#ifdef CVX_WARP_EXACT_SWEEP
         warp_sweep(S, lane, pk);
         if (lane < 10) S.L[lane] = S.T[lane * 11];
         __syncwarp();
+#else
+        warp_sweep_stale(S, lane, pk);
+#endif
         // ---- 7. slow problem: continue with a smaller penalty, once (rescale_rho) ---------
         const double rf = rescale_factor(it);
         if (rf > 0.0) {

@@ -16,7 +16,7 @@ for n_pts, n_lines in ((8, 4), (8, 0), (0, 6)):
     if n_lines:
         args.update(line_2d=torch.from_numpy(d["line_2d"]).to(dev), line_3d=torch.from_numpy(d["line_3d"]).to(dev))
     ws = cb.Workspace(B, dev)
-    for grace in (20, 40, 60, 80, 120, 200, -1):
+    for grace in (24, 32, 40, 48, 56, 64, 80, 100):
         if grace < 0 and n_lines == 6:
             continue
         out = None
