@@ -88,7 +88,7 @@ CVX_HD int64_t problem_resume(const double* h, Arr<S> V, Arr<S> M, Arr<S> L, QRT
 __constant__ signed char c_triples[15][10] = {CVX_TRIPLES(CVX_TRI_ROW)};
 #undef CVX_TRI_ROW
 
-struct WarpSmem {
+struct alignas(16) WarpSmem {
     double M[100], V[100], T[100], X[100], Z[100], Q[100];   // full 10x10, row-major
     double L[10], cs[10];
     double csall[90];   // (c, s) of the 45 pivot pairs of a sweep in round order (warp_sweep_stale)
@@ -207,10 +207,11 @@ __device__ __forceinline__ void warp_sweep(WarpSmem& S, int lane, const uint32_t
 // 52.8 -> 52.6, PnL-6 67.5 -> 68.1, PnP-8 53.8 -> 53.8, 4 points 121.4 -> 121.3, same poses (1e-9 rad), same problems at
 // the cap.  What it buys: the nine DEPENDENT rounds of (angle chain ~270 cycles + 2x2 block update + two warp barriers,
 // ~690 cycles each: half of the warp's iteration, profiles/r2bf) become one round of angles for all pairs on 32 + 13
-// lanes, nine rounds of plain row rotations of V, and the eigenvalues as diag(V' M V) from one product -- T itself
-// is not rotated at all.
-// On entry S.T = V' M V (full form); on exit S.V is rotated and S.L holds the new eigenvalue estimates; S.X is scratch.
-__device__ __forceinline__ void warp_sweep_stale(WarpSmem& S, int lane, const uint32_t pk[9])
+// lanes, the 45 rotations applied to register-resident rows of V and of M V by twenty lanes, and the eigenvalues as
+// column dot products of the two -- T itself is not rotated at all.
+// On entry S.T = V' M V (full form) and S.X = M V; on exit S.V is rotated (S.X with it) and S.L holds the new eigenvalue
+// estimates.
+__device__ __forceinline__ void warp_sweep_stale(WarpSmem& S, int lane)
 {
     // ---- angles: pivot pair number i = 5 * round + k, lanes take i = lane and i = lane + 32 ----------------------------
 #pragma unroll
@@ -226,39 +227,31 @@ __device__ __forceinline__ void warp_sweep_stale(WarpSmem& S, int lane, const ui
         }
     }
     __syncwarp();
-    // ---- nine rounds of row rotations of V: items (row lane / 5, pair lane % 5) and (row (lane + 32) / 5, pair (lane + 32) % 5)
-    const int kb = lane % 5, k1 = (lane + 32) % 5;
-    const int i0 = lane / 5, i1 = (lane + 32) / 5;
-#pragma unroll 1
-    for (int round = 0; round < 9; ++round) {
-        const int pb = (pk[round] >> 8) & 15, qb = (pk[round] >> 12) & 15, p1 = (pk[round] >> 16) & 15,
-                  q1 = (pk[round] >> 20) & 15;
-        {
-            const double c = S.csall[10 * round + 2 * kb], s = S.csall[10 * round + 2 * kb + 1];
-            const double vp = S.V[i0 * 10 + pb], vq = S.V[i0 * 10 + qb];
-            S.V[i0 * 10 + pb] = fma(c, vp, -s * vq);
-            S.V[i0 * 10 + qb] = fma(s, vp, c * vq);
-        }
-        if (lane < 18) {
-            const double c = S.csall[10 * round + 2 * k1], s = S.csall[10 * round + 2 * k1 + 1];
-            const double vp = S.V[i1 * 10 + p1], vq = S.V[i1 * 10 + q1];
-            S.V[i1 * 10 + p1] = fma(c, vp, -s * vq);
-            S.V[i1 * 10 + q1] = fma(s, vp, c * vq);
-        }
-        __syncwarp();
-    }
-    // ---- eigenvalue estimates: lambda_j = v_j' M v_j  (X = M V, then ten column dot products) --------------------------
-    for (int e = lane; e < 100; e += 32) {
-        const int r = e / 10, c = e - 10 * r;
-        double s0 = 0.0, s1 = 0.0;
+    // ---- the 45 rotations in cyclic order on the rows of V (lanes 0..9) and, alike, on the rows of X = M V (lanes
+    //      10..19; step 5 left it there): a row lives in registers, every pivot pair is a compile-time constant, so the
+    //      nine rounds need no barrier and no address arithmetic; X V-rotated is M V_new, which the eigenvalues need.
+    if (lane < 20) {
+        double* row = lane < 10 ? &S.V[lane * 10] : &S.X[(lane - 10) * 10];
+        double v[10];
 #pragma unroll
-        for (int k = 0; k < 10; k += 2) {
-            s0 = fma(S.M[r * 10 + k], S.V[k * 10 + c], s0);
-            s1 = fma(S.M[r * 10 + k + 1], S.V[(k + 1) * 10 + c], s1);
-        }
-        S.X[e] = s0 + s1;
+        for (int j = 0; j < 10; ++j) v[j] = row[j];
+        const double2* cs2 = reinterpret_cast<const double2*>(S.csall);
+#pragma unroll
+        for (int round = 0; round < 9; ++round)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                int p, q;
+                round_pair(round, k, p, q);
+                const double2 cs = cs2[5 * round + k];
+                const double vp = v[p], vq = v[q];
+                v[p] = fma(cs.x, vp, -cs.y * vq);
+                v[q] = fma(cs.y, vp, cs.x * vq);
+            }
+#pragma unroll
+        for (int j = 0; j < 10; ++j) row[j] = v[j];
     }
     __syncwarp();
+    // ---- eigenvalue estimates: lambda_j = v_j' M v_j = column j of V_new dot column j of M V_new -----------------------
     if (lane < 10) {
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -566,17 +559,24 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
         // ---- 5. T = V' M V  (M V into X, then the lower triangle of V' (M V), mirrored) ---
         for (int e = lane; e < 100; e += 32) {
             const int r = e / 10, c = e - 10 * r;
-            double s = 0.0;
+            double s0 = 0.0, s1 = 0.0;   // (two chains: half the dependent latency)
 #pragma unroll
-            for (int k = 0; k < 10; ++k) s = fma(S.M[r * 10 + k], S.V[k * 10 + c], s);
-            S.X[e] = s;
+            for (int k = 0; k < 10; k += 2) {
+                s0 = fma(S.M[r * 10 + k], S.V[k * 10 + c], s0);
+                s1 = fma(S.M[r * 10 + k + 1], S.V[(k + 1) * 10 + c], s1);
+            }
+            S.X[e] = s0 + s1;
         }
         __syncwarp();
         _Pragma("unroll") for (int q = 0; q < 2; ++q) if (q < np) {
             const int r = er[q], c = ec[q];
-            double s = 0.0;
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int k = 0; k < 10; ++k) s = fma(S.V[k * 10 + r], S.X[k * 10 + c], s);
+            for (int k = 0; k < 10; k += 2) {
+                s0 = fma(S.V[k * 10 + r], S.X[k * 10 + c], s0);
+                s1 = fma(S.V[(k + 1) * 10 + r], S.X[(k + 1) * 10 + c], s1);
+            }
+            const double s = s0 + s1;
             S.T[r * 10 + c] = s;
             S.T[c * 10 + r] = s;
         }
@@ -587,7 +587,7 @@ __device__ __noinline__ void warp_dr_loop(WarpSmem& S, const Opts& o, int lane, 
         if (lane < 10) S.L[lane] = S.T[lane * 11];
         __syncwarp();
 #else
-        warp_sweep_stale(S, lane, pk);
+        warp_sweep_stale(S, lane);
 #endif
         // ---- 7. slow problem: continue with a smaller penalty, once (rescale_rho) ---------
         const double rf = rescale_factor(it);
