@@ -14,10 +14,13 @@
 // Q/rho, rho, iteration count: one HAND slab entry) and leaves.  This kernel then
 // gives every such problem a whole WARP: the 10x10 matrices sit in shared memory in
 // full (unpacked) form, the 32 lanes split every step by matrix entry (Z = V L+ V',
-// the affine projection: one lane per equality, T = V'MV), the Jacobi sweep applies
-// the five disjoint rotations of a round at once as 25 independent 2x2 block updates
-// (two-sided) plus 50 row updates of V, and the Anderson dot products are spread over
-// 28 lanes.  One iteration costs ~5 k cycles (~2.5 us) instead of ~26 us.  The
+// the affine projection: one lane per equality, T = V'MV), the Jacobi sweep of a DR
+// iteration takes all 45 rotation angles from T as it is and applies them to
+// register-resident rows of V and M V (warp_sweep_stale; the cold decomposition of a
+// handed-back problem uses the exact round-by-round sweep, warp_sweep: the five disjoint
+// rotations of a round at once as 25 independent two-sided 2x2 block updates plus 50 row
+// updates of V), and the Anderson dot products are spread over 28 lanes.  One iteration
+// costs ~7 k cycles (3.55 us, measured on an idle GPU) instead of ~26 us.  The
 // algorithm, its constants and its stopping rule are those of the thread path; only
 // the Anderson history (FP32, unscaled, in shared memory) restarts at the hand-over.
 // When the DR loop of a problem has stopped the state goes back into its slab entry
