@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sides", action="store_true", help="skip the side_configs block")
-    ap.add_argument("--e2e-parts", type=int, default=3, help="sub-batches of the end-to-end step (HostStager(parts=...))")
+    ap.add_argument("--e2e-parts", default="3", help="sub-batches of the end-to-end step (HostStager(parts=...)): a count or "
+                                                     "comma-separated fractions, e.g. 0.2,0.4,0.4")
     ap.add_argument("--admm", default="f64", choices=["f64", "f32"],
                     help="f64: FP64 ADMM throughout (the headline, BASELINE.json configs[2]); f32: FP32 first "
                          "phase + FP64 tail and extraction (configs[3]), a side measurement")
@@ -413,7 +414,8 @@ def run_ours(a):
     # ... and the same entry point with parts=N: the batch as N independent sub-batch solves on their own streams;
     # sub-batch p starts when its slice has arrived and its rows go back to the host under the kernels of the next
     # ones (HostStager docstring).  Same bytes up and down inside the timed region; this is the e2e headline.
-    stager_p = cb.HostStager(K, dev, parts=a.e2e_parts, admm_dtype=a.admm)
+    e2e_parts = tuple(float(x) for x in a.e2e_parts.split(",")) if "," in a.e2e_parts else int(a.e2e_parts)
+    stager_p = cb.HostStager(K, dev, parts=e2e_parts, admm_dtype=a.admm)
 
     def step_e2e():
         o = stager_p.solve(host, record=gat.local, host_record=host_out)
@@ -583,7 +585,7 @@ def run_ours(a):
                        "host_affinity": numa},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / a.steps,
-                    "what": f"cvxpnpl_b200.HostStager(parts={a.e2e_parts}).solve(host tensors, host_record=...): pinned host "
+                    "what": f"cvxpnpl_b200.HostStager(parts={e2e_parts}).solve(host tensors, host_record=...): pinned host "
                             "correspondences in, pinned host [B,15] pose rows out, the batch as independent sub-batch "
                             "solves on their own streams (copies of later sub-batches and rows of earlier ones under "
                             "the kernels)",

@@ -107,7 +107,15 @@ class HostStager:
         self.device = torch.device(device)
         self.K = torch.as_tensor(K, dtype=torch.float64).to(self.device)
         self.chunks = int(chunks)
-        self.parts = max(1, int(parts))
+        # parts: a count (equal sub-batches) or a sequence of fractions of the batch, e.g. (0.2, 0.4, 0.4): a short
+        # first sub-batch lets the kernels start sooner
+        if isinstance(parts, (tuple, list)):
+            tot = float(sum(parts))
+            self.part_fracs = [float(f) / tot for f in parts]
+            self.parts = len(self.part_fracs)
+        else:
+            self.parts = max(1, int(parts))
+            self.part_fracs = [1.0 / self.parts] * self.parts
         self.kw = solve_kwargs
         self.copy_stream = torch.cuda.Stream(self.device)
         self.buf = None
@@ -120,7 +128,11 @@ class HostStager:
 
     def _solve_parts(self, host, B, record, host_record) -> BatchedPoses:
         dev, P = self.device, self.parts
-        bounds = [(p * B) // P for p in range(P + 1)]
+        acc, bounds = 0.0, [0]
+        for f in self.part_fracs[:-1]:
+            acc += f
+            bounds.append(min(B, int(round(acc * B))))
+        bounds.append(B)
         if self.buf is None or self.buf.keys() != host.keys() or any(self.buf[k].shape != v.shape for k, v in host.items()):
             self.buf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
             self.part_ws = self.part_out = None
