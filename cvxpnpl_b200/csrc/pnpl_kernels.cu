@@ -254,8 +254,15 @@ enum {
     CTRL_TRK_NEXT = 8,   // queue head of the tracked solver
     CTRL_TRK_DONE = 9,   // CTAs of the tracked solver that have finished (the concurrent service kernel stops then)
     CTRL_SVC_NEXT = 10,  // tickets (entries of fail_list) taken by the concurrent service kernel
-    CTRL_NSTRAG_START = 11   // slab entries that exist when straggler_kernel starts (snapshot of CTRL_NSTRAG)
+    CTRL_NSTRAG_START = 11,  // slab entries that exist when straggler_kernel starts (snapshot of CTRL_NSTRAG)
+    CTRL_NSERVED = 12        // entries of fail_list the concurrent service kernel has served
 };
+// hand-backs of the tracked solver that nobody has served yet (valid once the service kernel has finished)
+__device__ __forceinline__ unsigned long long unserved_handbacks(const unsigned long long* ctrl)
+{
+    const unsigned long long n = ctrl[CTRL_NFAIL], s = ctrl[CTRL_NSERVED];
+    return n > s ? n - s : 0ULL;
+}
 
 // RESUME = false: the batch.  Lanes pull problems from ctrl[CTRL_NEXT]; once that queue
 //   is empty, a lane whose problem is still in its DR loop `grace` passes later hands it
@@ -278,7 +285,7 @@ solve_fused_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, const 
     // list modes: nothing handed over / handed back (the common case on well-posed batches) -> leave before the
     // tensor-memory allocation; a CTA beyond the list's length has nothing to do either
     if ((RESUME || from_track) && (unsigned long long)blockIdx.x * NT >= ctrl[RESUME ? CTRL_NSTRAG : CTRL_NFAIL]) return;
-    if (from_track > 1 && ctrl[CTRL_NFAIL] <= (unsigned long long)(from_track - 1)) return;   // (from_track = 1 + direct_max)
+    if (from_track > 1 && unserved_handbacks(ctrl) <= (unsigned long long)(from_track - 1)) return;   // (from_track = 1 + direct_max)
 
     cvx::Arr<NT> V{smem + tid};
     cvx::Arr<NT> M{smem + (size_t)100 * NT + tid};
@@ -577,7 +584,7 @@ __device__ __forceinline__ bool cta_vote_and(bool f)
 constexpr int SLOW_IT = CVX_SLOW_IT;
 __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_desc& d, const Opts& o, unsigned long long* ctrl,
                                             double* pre, double* park, const double* warm, const int32_t* order,
-                                            int32_t* fail_list, int grace, int handoff_max, bool svc_on, double* smem,
+                                            int32_t* fail_list, int grace, int handoff_max, int slow_it, double* smem,
                                             uint32_t tmem_base, int* queue_dry)
 {
     const int p = threadIdx.x & (NT - 1);
@@ -654,7 +661,7 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
                     ctl = -3.0;
                 // a slow problem moves to the concurrent service kernel (a warp of its own: ~6.5 us per iteration
                 // instead of one ~12 us pass) if a service warp is waiting for work right now
-                if (svc_on && st.it >= SLOW_IT && st.it % 25 == 0 &&
+                if (slow_it > 0 && st.it >= slow_it && st.it % 25 == 0 &&
                     *(volatile unsigned long long*)(ctrl + CTRL_SVC_NEXT) > *(volatile unsigned long long*)(ctrl + CTRL_NFAIL))
                     ctl = -3.0;
             }
@@ -718,7 +725,7 @@ solve_track2_kernel(cvxpnpl_b200_desc d, Opts o, unsigned long long* ctrl, doubl
     __shared__ int queue_dry;
     if (threadIdx.x == 0) queue_dry = 0;
     const uint32_t tmem_base = tmem_alloc_all(&tmem_slot);
-    track2_loop(threadIdx.x < NT ? 0 : 1, d, o, ctrl, pre, park, warm, order, fail_list, grace, handoff_max, svc_on != 0, smem,
+    track2_loop(threadIdx.x < NT ? 0 : 1, d, o, ctrl, pre, park, warm, order, fail_list, grace, handoff_max, svc_on, smem,
                 tmem_base, &queue_dry);
     if (threadIdx.x == 0) {
         __threadfence();
@@ -736,7 +743,7 @@ __global__ void __launch_bounds__(NT_R) redecomp_kernel(const unsigned long long
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
-    if (ctrl[CTRL_NFAIL] <= (unsigned long long)direct_max) return;   // few: straight to the warp-per-problem kernel
+    if (unserved_handbacks(ctrl) <= (unsigned long long)direct_max) return;   // few: straight to the warp-per-problem kernel
     for (unsigned long long k = (unsigned long long)blockIdx.x * NT_R + tid; k < ctrl[CTRL_NFAIL];
          k += (unsigned long long)gridDim.x * NT_R) {
     const int64_t b = fail_list[k];
@@ -916,7 +923,7 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
     cvx::WarpSmem& S = reinterpret_cast<cvx::WarpSmem*>(smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned long long n_fail = fail_list ? ctrl[CTRL_NFAIL] : 0ULL;
-    const bool direct = n_fail > 0 && n_fail <= (unsigned long long)direct_max;
+    const bool direct = n_fail > 0 && unserved_handbacks(ctrl) <= (unsigned long long)direct_max;   // (served entries are skipped)
     // tickets: first the slab entries that exist when this kernel starts (hand-overs of the thread solver; problems the
     // service kernel gave back unfinished), then -- DIRECT mode -- the entries of the hand-back list nobody has served
     const unsigned long long n_slab = *(volatile unsigned long long*)(ctrl + CTRL_NSTRAG_START);
@@ -986,7 +993,8 @@ constexpr int NT_SVC = 512;
 constexpr int N_SVC_CTAS = 2;       // SMs reserved for the service kernel
 constexpr int N_SVC_CTAS_FEW = 6;   // ... for problems with fewer than 10 correspondences, whose batches hold more slow problems
                                     // (1e5 PnP-8: 6.79 ms with two, 5.81 with four, 5.56 with six; PnPL 8+4: 5.08 / 5.12 / --)
-constexpr int SVC_ITERS = 400;   // iterations a service warp spends on one problem
+constexpr int SVC_ITERS = 1 << 20;   // iterations a service warp may spend on one problem: no limit (a cap of 400 was
+                                     // measured: the same or slower on every family once the warp iteration took 3.55 us)
 constexpr size_t SMEM_SVC_BYTES = (NT_SVC / 32) * sizeof(cvx::WarpSmem);   // > half an SM: one CTA per SM
 __global__ void __launch_bounds__(NT_SVC, 1) service_kernel(Opts o, unsigned long long* ctrl, int32_t* fail_list, const double* pre,
                                                             double* slab, unsigned n_track_ctas, unsigned long long limit_ns,
@@ -1036,6 +1044,7 @@ __global__ void __launch_bounds__(NT_SVC, 1) service_kernel(Opts o, unsigned lon
         if (lane == 0) {
             __threadfence();
             *(volatile int32_t*)(fail_list + k) = -2 - b;   // served (finished, or parked unfinished in the slab)
+            atomicAdd(ctrl + CTRL_NSERVED, 1ULL);
         }
     }
 }
@@ -1888,6 +1897,11 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         // desc.handoff < 0 (no warp-per-problem kernels at all) switches it off.
         static const bool no_service = getenv("CVXPNPL_B200_NO_SERVICE") != nullptr;   // (diagnostics)
         static const int svc_iters = getenv("CVXPNPL_B200_SVC_ITERS") ? atoi(getenv("CVXPNPL_B200_SVC_ITERS")) : SVC_ITERS;
+        static const int slow_it_env = getenv("CVXPNPL_B200_SLOW_IT") ? atoi(getenv("CVXPNPL_B200_SLOW_IT")) : 0;
+        // a slow problem moves to an idle service warp from this iteration on: 100 where that is rare (PnPL 8+4: p99 = 74),
+        // 200 for the families with fewer than 10 correspondences, whose idle warps would otherwise go to the many problems
+        // that need 100-150 iterations instead of the few that need 1000 (1e5 problems, 5 points + 3 lines: 8.0 -> 7.2 ms)
+        const int slow_it = slow_it_env > 0 ? slow_it_env : (d->n_pts + d->n_lines < 10 ? 2 * SLOW_IT : SLOW_IT);
         SideStream* side = (grace >= 0 && d->psd_mode != 2 && !no_service) ? side_for_current_device() : nullptr;
         const bool svc_on = side != nullptr;
         // families whose batches hold more slow problems (fewer than 10 correspondences) get a wider service
@@ -1911,7 +1925,7 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         else
             solve_track2_kernel<<<(unsigned)blocks_trk, NT2, SMEM_TRK2_BYTES, st>>>(dd, o, ctrl, pre, park, warm_in, order,
                                                                                     fail_list, track_grace, handoff_max,
-                                                                                    svc_on ? 1 : 0);
+                                                                                    svc_on ? slow_it : 0);
         if (svc_on) {
             cudaEventRecord(side->join, side->stream);
             cudaStreamWaitEvent(st, side->join, 0);
