@@ -614,7 +614,7 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
         H.wait_st();
     }
     if (ROLE == 0) G[55] = 0.0;
-    int64_t b = -1;
+    int64_t b = -1, b_next = -1;
     bool exhausted = false, counted = false, dry_known = false;
     int drain = 0;
     const unsigned long long n_work = (unsigned long long)d.batch;
@@ -637,8 +637,38 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
         bool fresh = false;
         if (ROLE == 0) {
             double ctl = -1.0;
+#ifndef CVX_NO_PREFETCH
+            // A problem whose DR loop is over only polishes its eigenpairs for one to four more passes: its lane takes the
+            // NEXT problem off the queue now and prefetches that record, so the loads of t2_begin -- which hold the lane's
+            // warp pair, and through the per-pass meeting the whole CTA, for an L2 / HBM round trip in nearly every pass --
+            // find it in L1.
+            if (b >= 0 && b_next < 0 && !exhausted && st.finite && !st.iterating) {
+                const unsigned long long nb = atomicAdd(ctrl + CTRL_TRK_NEXT, 1ULL);
+                if (nb < n_work) {
+                    b_next = (int64_t)order[nb];
+                    const char* r0 = reinterpret_cast<const char*>(pre + b_next * cvx::PRE_DOUBLES);
+#pragma unroll
+                    for (int l = 0; l < (cvx::TRK_DOUBLES * 8 + 127) / 128 + 1; ++l)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(r0 + 128 * l));
+                    if (warm) {
+                        const char* w0 = reinterpret_cast<const char*>(warm + b_next * cvx::WARM_DOUBLES);
+#pragma unroll
+                        for (int l = 0; l < (cvx::WARM_DOUBLES * 8 + 127) / 128 + 1; ++l)
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(w0 + 128 * l));
+                    }
+                } else {
+                    exhausted = true;
+                    *queue_dry = 1;
+                }
+            }
+#endif
             if (b < 0) {
-                if (!exhausted) {
+                if (b_next >= 0) {
+                    b = b_next;
+                    b_next = -1;
+                    ctl = (double)b;
+                    fresh = true;
+                } else if (!exhausted) {
                     const unsigned long long nb = atomicAdd(ctrl + CTRL_TRK_NEXT, 1ULL);
                     if (nb < n_work) {
                         b = (int64_t)order[nb];
