@@ -30,6 +30,36 @@ def load():
     return _lib
 
 
+def load_variant(tag, defines):
+    """A second build of the harness with extra -D flags (algorithm variants compared against the default build);
+    returns a context manager that routes the functions of this module to it."""
+    import contextlib
+    so = os.path.join(_HERE, "_build", f"libhost_{tag}.so")
+    srcs = [os.path.join(_HERE, "host_harness.cpp")] + [
+        os.path.join(_ROOT, "cvxpnpl_b200", "csrc", f) for f in ("pnpl_core.cuh", "pnpl_dr.inl", "pnpl_extract.cuh", "pnpl_solve.cuh", "pnpl_track.cuh", "pnpl_track2.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread"] + [f"-D{x}" for x in defines] + ["-o", so, srcs[0]])
+    variant = ctypes.CDLL(so)
+
+    @contextlib.contextmanager
+    def use():
+        global _lib
+        load()
+        keep, _lib_new = _lib, variant
+        _set(_lib_new)
+        try:
+            yield
+        finally:
+            _set(keep)
+    return use
+
+
+def _set(lib):
+    global _lib
+    _lib = lib
+
+
 def solve(d, eps=1e-9, max_iters=2500, sweeps=0, rho_rel=0.0, alpha=0.0, sigma=0.0, anderson=1, variant=0, fp32_iters=0):
     lib = load()
     B, n_pts, n_lines = d["pts_2d"].shape[0], d["pts_2d"].shape[1], d["line_2d"].shape[1]
