@@ -689,7 +689,7 @@ __device__ __forceinline__ void track2_loop(const int ROLE, const cvxpnpl_b200_d
                 }
                 if (drain > grace && *(volatile unsigned long long*)(ctrl + CTRL_ACTIVE) <= (unsigned long long)handoff_max)
                     ctl = -3.0;
-                // a slow problem moves to the concurrent service kernel (a warp of its own: ~6.5 us per iteration
+                // a slow problem moves to the concurrent service kernel (a warp of its own: ~3.6 us per iteration
                 // instead of one ~12 us pass) if a service warp is waiting for work right now
                 if (slow_it > 0 && st.it >= slow_it && st.it % 25 == 0 &&
                     *(volatile unsigned long long*)(ctrl + CTRL_SVC_NEXT) > *(volatile unsigned long long*)(ctrl + CTRL_NFAIL))
@@ -1918,9 +1918,10 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
     const int direct_max = (tracked && grace >= 0) ? handoff_max : 0;
     if (tracked) {
         mark(tm, 7, st);
-        // Stragglers of the tracked solver: one of its passes takes ~13 us, an iteration of the warp-per-problem kernel
-        // ~6.7 us, and the detour (cold decomposition, hand-over, resume) costs ~0.3 ms: handing over earlier than 64
-        // passes after the queue ran dry does not pay (1e5 PnPL 8+4: 1600 hand-overs at grace 40, 16 at 64).
+        // Stragglers of the tracked solver: one of its passes takes ~10 us, an iteration of the warp-per-problem kernel
+        // ~3.6 us, and the detour (cold decomposition, hand-over, resume) costs ~0.3 ms: handing over earlier than 64
+        // passes after the queue ran dry does not pay (1e5 PnPL 8+4, re-swept with the current kernels, profiles/README
+        // r2cc: grace 24..48 5.08 ms with ~2000 hand-overs, 56 4.92, 64..100 4.81 with ~55).
         const int track_grace = d->handoff != 0 ? grace : 64;
         // The concurrent service kernel (side stream): two SMs -- left free by a grid of n_sm - 2 CTAs when the batch
         // fills the GPU -- finish handed-back problems warp per problem while the bulk is still being solved.
