@@ -1920,8 +1920,8 @@ static int solve_impl(const cvxpnpl_b200_desc* d, void* stream, int mode, int64_
         mark(tm, 7, st);
         // Stragglers of the tracked solver: one of its passes takes ~10 us, an iteration of the warp-per-problem kernel
         // ~3.6 us, and the detour (cold decomposition, hand-over, resume) costs ~0.3 ms: handing over earlier than 64
-        // passes after the queue ran dry does not pay (1e5 PnPL 8+4, re-swept with the current kernels, profiles/README
-        // r2cc: grace 24..48 5.08 ms with ~2000 hand-overs, 56 4.92, 64..100 4.81 with ~55).
+        // passes after the queue ran dry does not pay (1e5 PnPL 8+4, re-swept with the pair-barrier kernel,
+        // profiles/r2cc_grace_sweep.txt: grace 24..48 5.08 ms with ~2000 hand-overs, 56 4.92, 64..100 4.81 with ~55).
         const int track_grace = d->handoff != 0 ? grace : 64;
         // The concurrent service kernel (side stream): two SMs -- left free by a grid of n_sm - 2 CTAs when the batch
         // fills the GPU -- finish handed-back problems warp per problem while the bulk is still being solved.
