@@ -81,6 +81,17 @@ class HostPipeline:
         return self.host_out
 
 
+def part_bounds(B, fracs):
+    """Contiguous sub-batch boundaries [0, ..., B] for the fractions `fracs` (normalised, monotone, exact at both ends)."""
+    tot = float(sum(fracs))
+    acc, bounds = 0.0, [0]
+    for f in list(fracs)[:-1]:
+        acc += float(f) / tot
+        bounds.append(max(bounds[-1], min(B, int(round(acc * B)))))
+    bounds.append(B)
+    return bounds
+
+
 class HostStager:
     """One batch from pinned HOST memory with the copy hidden as far as a single step allows.
 
@@ -128,11 +139,7 @@ class HostStager:
 
     def _solve_parts(self, host, B, record, host_record) -> BatchedPoses:
         dev, P = self.device, self.parts
-        acc, bounds = 0.0, [0]
-        for f in self.part_fracs[:-1]:
-            acc += f
-            bounds.append(min(B, int(round(acc * B))))
-        bounds.append(B)
+        bounds = part_bounds(B, self.part_fracs)
         if self.buf is None or self.buf.keys() != host.keys() or any(self.buf[k].shape != v.shape for k, v in host.items()):
             self.buf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
             self.part_ws = self.part_out = None

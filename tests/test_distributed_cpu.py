@@ -70,3 +70,16 @@ def test_gloo_world2_gather(total):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_host_stager_part_bounds():
+    """HostStager(parts=...): sub-batch boundaries are contiguous, monotone and cover the batch for counts and fractions,
+    ragged and tiny batches included (pure host logic)."""
+    from cvxpnpl_b200.pipeline import part_bounds
+    for B in (0, 1, 7, 100000, 30001):
+        for fr in ([1, 1, 1], [0.3, 0.7], [0.15, 0.45, 0.4], [1.0], [5, 1, 1, 1, 1, 1]):
+            b = part_bounds(B, fr)
+            assert b[0] == 0 and b[-1] == B and len(b) == len(fr) + 1
+            assert all(x <= y for x, y in zip(b[:-1], b[1:]))
+    assert part_bounds(100000, [1, 1, 1]) == [0, 33333, 66667, 100000]
+    assert part_bounds(100000, [0.3, 0.7]) == [0, 30000, 100000]
