@@ -1021,8 +1021,11 @@ __global__ void __launch_bounds__(NT_W, 2) straggler_kernel(Opts o, unsigned lon
 // ---------------------------------------------------------------------------------
 constexpr int NT_SVC = 512;
 constexpr int N_SVC_CTAS = 2;       // SMs reserved for the service kernel
-constexpr int N_SVC_CTAS_FEW = 6;   // ... for problems with fewer than 10 correspondences, whose batches hold more slow problems
-                                    // (1e5 PnP-8: 6.79 ms with two, 5.81 with four, 5.56 with six; PnPL 8+4: 5.08 / 5.12 / --)
+constexpr int N_SVC_CTAS_FEW = 2;   // ... for problems with fewer than 10 correspondences.  Their batches hold more slow
+                                    // problems, and while a warp iteration took 6.2 us six SMs paid (1e5 PnP-8: 6.79 ms with two,
+                                    // 5.81 with four, 5.56 with six).  At 3.55 us per iteration two SMs serve them as well and the
+                                    // bulk keeps the other four (profiles/r2ce: PnP-8 5.04 / 5.11 / 5.14 ms with 2 / 4 / 6, 5 points +
+                                    // 3 lines 7.04 / 7.13 / 7.18, 8 lines 7.3-8.1 / 7.8 / 9.7, PnL-6 15.9 with any).
 constexpr int SVC_ITERS = 1 << 20;   // iterations a service warp may spend on one problem: no limit (a cap of 400 was
                                      // measured: the same or slower on every family once the warp iteration took 3.55 us)
 constexpr size_t SMEM_SVC_BYTES = (NT_SVC / 32) * sizeof(cvx::WarpSmem);   // > half an SM: one CTA per SM
